@@ -1,0 +1,146 @@
+/*
+ * richmol_b200 -- C ABI of the B200-native TDSE propagation hot path.
+ *
+ * This is the drop-in boundary ("Boundary").  The reference (CFEL-CMI/richmol) is pure
+ * Python; the seams this library replaces are the Python methods listed next to each entry point
+ * (file:line relative to the reference tree) plus the one native FFI the reference already has on
+ * this path, the f2py `expokit.zhexpv` Krylov exponential (expokit/expokit.pyf:200-216), whose role
+ * `rmb_propagate_step` takes over.  INTEGRATION.md shows the ctypes stub a richmol maintainer
+ * would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature.  `stream` arguments are a
+ *     `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - all complex data is interleaved (re, im) IEEE double = numpy complex128.
+ *   - state batches are state-major: `psi[s * ld + i]`, i < N, exactly the `(nstates, N)`
+ *     C-contiguous layout `TDSE.update` receives (richmol/tdse.py:375,397).
+ *   - `*_dev` pointers are device pointers owned by the caller (e.g. `torch.Tensor.data_ptr()`);
+ *     the library never frees them.  `*_host` pointers are host memory.
+ *   - every function returns RMB_OK (0) or a negative status; `rmb_last_error()` gives the text.
+ *   - one host thread per GPU; a handle is bound to the device current at creation.
+ */
+#ifndef RICHMOL_B200_H
+#define RICHMOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMB_ABI_VERSION 1
+
+enum {
+    RMB_OK = 0,
+    RMB_ERR_INVALID = -1,    /* bad argument / inconsistent tables            -> ValueError        */
+    RMB_ERR_CUDA = -2,       /* CUDA runtime failure (no device, OOM, launch) -> RuntimeError      */
+    RMB_ERR_MAXORDER = -3,   /* Lanczos hit `maxorder` (richmol/tdse.py:480-484) -> ValueError     */
+    RMB_ERR_NOFIELD = -4     /* operator part has no field applied (richmol/field.py:1163-1169)    */
+};
+
+/* One term of a (lazily summed) operator: a CarTens with K and M factors
+ * (data model: richmol/field.py:58-170; sum: richmol/field.py:951-1070).                          */
+typedef struct rmb_part_desc {
+    int32_t ncart;             /* number of Cartesian components carrying M coefficients           */
+    int32_t nprod;             /* number of (Jpair, sympair, irrep) block products                 */
+    const int32_t* pr_bra;     /* [nprod] bra (J,sym) block index                                  */
+    const int32_t* pr_ket;     /* [nprod] ket (J,sym) block index                                  */
+    const int32_t* pr_table;   /* [nprod] M-table index (identical M factors are stored once)      */
+    const int64_t* pr_koff;    /* [nprod] offset of the dense row-major dk1 x dk2 K block in kpool,
+                                  counted in K elements                                            */
+    int32_t k_is_complex;      /* 0: kpool holds doubles, 1: interleaved complex                   */
+    const double* kpool;
+    int64_t kpool_len;         /* number of K elements in kpool                                    */
+    int32_t ntables;
+    const int32_t* tb_dm1;     /* [ntables] rows (bra m quanta)                                    */
+    const int32_t* tb_dm2;     /* [ntables] columns (ket m quanta)                                 */
+    const int32_t* tb_nd;      /* [ntables] ELL width = max entries per row of the union pattern   */
+    const int64_t* tb_off;     /* [ntables+1] entry offset; table t has tb_dm1[t]*tb_nd[t] entries,
+                                  row-major (m1, j)                                                */
+    const int32_t* ent_col;    /* [nent] ket m index of the entry, -1 = padding                    */
+    const double* ent_coef;    /* [ncart][nent] complex: M_{cart} value at the entry               */
+} rmb_part_desc;
+
+typedef struct rmb_operator_desc {
+    int32_t nblocks;           /* (J,sym) blocks in `for J in Jlist2 for sym in symlist2[J]` order
+                                  (richmol/tdse.py:343-348)                                         */
+    const int64_t* blk_off;    /* [nblocks+1] offset of the block in the flat state vector          */
+    const int32_t* blk_dm;     /* [nblocks] dim_m; block index = im*dim_k + ik (m-major)            */
+    const int32_t* blk_dk;     /* [nblocks] dim_k                                                   */
+    int32_t nparts;
+    const rmb_part_desc* parts;
+} rmb_operator_desc;
+
+typedef struct rmb_operator rmb_operator;   /* opaque; owns device copies of the tables */
+
+int32_t rmb_abi_version(void);
+const char* rmb_last_error(void);
+/* number of visible CUDA devices, or a negative status */
+int32_t rmb_device_count(void);
+
+/* Upload the block tables of an operator.  Replaces the per-call dict walking of
+ * CarTens.vec (richmol/field.py:1212-1243).                                                         */
+int32_t rmb_operator_create(const rmb_operator_desc* desc, rmb_operator** out);
+void rmb_operator_destroy(rmb_operator* op);
+int64_t rmb_operator_dim(const rmb_operator* op);            /* N                                   */
+int64_t rmb_operator_nentries(const rmb_operator* op, int32_t part);
+
+/* K1 -- CarTens.field (richmol/field.py:1073-1142):  MF = sum_cart fprod[cart] * M_cart on the
+ * device, |MF| < thresh zeroed (thresh <= 0: no element threshold).  `fprod[ncart]` are the
+ * products of field components per Cartesian label, already screened by the caller (a dropped
+ * product is passed as 0).  `all_dropped` != 0 reproduces the early return of field.py:1107-1112
+ * (empty mfmat).                                                                                    */
+int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fprod,
+                               double thresh, int32_t all_dropped, void* stream);
+/* Copy the contracted MF entries of a part back (for the `mfmat` attribute), [nent] complex.        */
+int32_t rmb_operator_get_mf(rmb_operator* op, int32_t part, double* out_host, void* stream);
+/* 1 if any MF entry of any part is non-zero (len(H.mfmat) > 0, richmol/tdse.py:377); syncs.         */
+int32_t rmb_operator_mf_nonempty(rmb_operator* op, void* stream);
+
+/* K2 -- CarTens.vec (richmol/field.py:1145-1245) for a batch of states:
+ * y[s] = sum_products (MF (x) K) x[s].  x_dev != y_dev.                                             */
+int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t nstates,
+                   int64_t ld, void* stream);
+
+/* K3+K4 -- TDSE.update (richmol/tdse.py:265-414) with propag='internal'
+ * (_expmv_lanczos, richmol/tdse.py:417-486) for every row of psi, in place:
+ *     psi <- ph * exp(fac * H) * (ph * psi)          ph = h0phase_dev (may be NULL: no split)
+ * with the reference's recurrences and stopping rule (sum |u_k - u_{k-1}|^2 <= tol, at most
+ * `maxorder` basis vectors).  orders_host (may be NULL) receives per state the index of the last
+ * Lanczos iteration (= matvecs - 1).  Returns RMB_ERR_MAXORDER if any state reached maxorder.
+ * If `skip_krylov` != 0 only the two phase multiplications are applied (richmol/tdse.py:377).        */
+int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld,
+                           double fac_re, double fac_im, double tol, int32_t maxorder,
+                           const double* h0phase_dev, int32_t skip_krylov,
+                           int32_t* orders_host, void* stream);
+/* Same, with HOST buffers: copies psi in, propagates, copies the result out (this is the call a
+ * numpy-array caller of TDSE.update makes; used for the end-to-end figure).  h0phase_host may be
+ * NULL.                                                                                             */
+int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
+                                int64_t nstates, int64_t ld, double fac_re, double fac_im,
+                                double tol, int32_t maxorder, const double* h0phase_host,
+                                int32_t skip_krylov, int32_t* orders_host, void* stream);
+
+/* K5 -- observables (user code in examples/ocs_alignment.py:99-100, tests/test_tdse.py:66).
+ * expval_dev[s] = <psi_s| O |psi_s>  (complex, [nstates]), O given as an operator whose field has
+ * been applied (rank-0 tensors: fprod = {1}).                                                       */
+int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates, int64_t ld,
+                        double* expval_dev, void* stream);
+/* pop_dev[i] = sum_s |psi_s[i]|^2  ([N] doubles).                                                   */
+int32_t rmb_populations(const double* psi_dev, int64_t nstates, int64_t n, int64_t ld,
+                        double* pop_dev, void* stream);
+
+/* Tuning / diagnostics (not part of the reference seam). */
+/* workspace budget in bytes for the Krylov vectors of one sub-batch (default: 40% of free memory) */
+int32_t rmb_set_workspace_budget(rmb_operator* op, int64_t bytes);
+/* counters since handle creation: [0] kernel launches, [1] matvec launches, [2] Lanczos
+ * iterations (batch-level), [3] state-matvecs                                                       */
+int32_t rmb_get_counters(const rmb_operator* op, int64_t* out4);
+/* device time (ms, CUDA events on `stream`) spent inside matvec launches since the last reset, and
+ * the number of launches it covers; enabling timing serialises with event syncs at query time only */
+int32_t rmb_matvec_timing(rmb_operator* op, int32_t enable, double* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RICHMOL_B200_H */

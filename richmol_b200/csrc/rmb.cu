@@ -1,0 +1,711 @@
+// Host side of librichmol_b200.so: the C ABI declared in include/richmol_b200.h.
+// Operator upload + work decomposition, kernel launches, the Lanczos driver loop.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+
+#include "rmb_kernels.cuh"
+
+namespace rmb {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return RMB_ERR_CUDA;
+}
+
+template <typename T>
+static int upload(T** dptr, const T* src, size_t count) {
+    *dptr = nullptr;
+    if (count == 0) count = 1;   // keep pointers valid
+    RMB_CUDA(cudaMalloc((void**)dptr, count * sizeof(T)));
+    if (src) RMB_CUDA(cudaMemcpy(*dptr, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return RMB_OK;
+}
+
+static inline int nchunks(long long n) { return (int)((n + VEC_CHUNK - 1) / VEC_CHUNK); }
+
+}  // namespace rmb
+
+using namespace rmb;
+
+extern "C" {
+
+int32_t rmb_abi_version(void) { return RMB_ABI_VERSION; }
+
+const char* rmb_last_error(void) { return g_error.c_str(); }
+
+int32_t rmb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDeviceCount");
+        return RMB_ERR_CUDA;
+    }
+    return n;
+}
+
+void rmb_operator_destroy(rmb_operator* op) {
+    if (!op) return;
+    cudaFree(op->d_prods);
+    cudaFree(op->d_items);
+    cudaFree(op->d_ent_col);
+    cudaFree(op->d_ent_val);
+    cudaFree(op->d_kpool);
+    cudaFree(op->d_flags);
+    for (auto& p : op->parts) {
+        cudaFree(p.d_coef);
+        cudaFree(p.d_fprod);
+    }
+    for (auto* s : op->slabs) cudaFree(s);
+    cudaFree(op->d_w);
+    cudaFree(op->d_W);
+    cudaFree(op->d_slab_ptrs);
+    cudaFree(op->d_alpha);
+    cudaFree(op->d_beta);
+    cudaFree(op->d_ccur);
+    cudaFree(op->d_dc);
+    cudaFree(op->d_active);
+    cudaFree(op->d_order);
+    cudaFree(op->d_pdot);
+    cudaFree(op->d_pnrm);
+    cudaFree(op->d_pconv);
+    cudaFree(op->d_ctrl);
+    if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
+    cudaFree(op->d_stage);
+    cudaFree(op->d_phase);
+    for (auto& e : op->mv_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    for (auto& e : op->mv_event_pool) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    delete op;
+}
+
+int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
+    if (!d || !out) {
+        set_error("null descriptor");
+        return RMB_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (d->nblocks <= 0 || d->nparts < 0) {
+        set_error("operator needs at least one (J,sym) block");
+        return RMB_ERR_INVALID;
+    }
+    int ndev = 0;
+    RMB_CUDA(cudaGetDeviceCount(&ndev));
+    rmb_operator* op = new rmb_operator();
+    struct Guard {
+        rmb_operator* p;
+        ~Guard() { if (p) rmb_operator_destroy(p); }
+    } guard{op};
+    RMB_CUDA(cudaGetDevice(&op->device));
+    RMB_CUDA(cudaDeviceGetAttribute(&op->num_sms, cudaDevAttrMultiProcessorCount, op->device));
+    op->nblocks = d->nblocks;
+    op->n = d->blk_off[d->nblocks];
+    for (int b = 0; b < d->nblocks; ++b) {
+        if (d->blk_off[b + 1] - d->blk_off[b] != (long long)d->blk_dm[b] * d->blk_dk[b]) {
+            set_error("block offsets inconsistent with dim_m*dim_k");
+            return RMB_ERR_INVALID;
+        }
+        op->dk_max = std::max(op->dk_max, d->blk_dk[b]);
+    }
+    // ---- merge parts: global entry pool, global K pool (complex if any part is complex)
+    bool kc = false;
+    for (int q = 0; q < d->nparts; ++q) kc = kc || d->parts[q].k_is_complex;
+    op->k_complex = kc;
+    std::vector<int> ent_col;
+    std::vector<double> kpool;
+    struct HProd { int bra, ket; long long koff, ent_off; int nd; };
+    std::vector<HProd> hp;
+    op->parts.resize(d->nparts);
+    for (int q = 0; q < d->nparts; ++q) {
+        const rmb_part_desc& pd = d->parts[q];
+        PartH& ph = op->parts[q];
+        ph.ncart = pd.ncart;
+        const long long nent = pd.tb_off ? pd.tb_off[pd.ntables] : 0;
+        ph.ent_begin = (long long)ent_col.size();
+        ph.ent_end = ph.ent_begin + nent;
+        ent_col.insert(ent_col.end(), pd.ent_col, pd.ent_col + nent);
+        const long long kbase = (long long)(kc ? kpool.size() / 2 : kpool.size());
+        if (kc && !pd.k_is_complex) {
+            for (long long i = 0; i < pd.kpool_len; ++i) {
+                kpool.push_back(pd.kpool[i]);
+                kpool.push_back(0.0);
+            }
+        } else {
+            kpool.insert(kpool.end(), pd.kpool, pd.kpool + pd.kpool_len * (pd.k_is_complex ? 2 : 1));
+        }
+        for (int t = 0; t < pd.ntables; ++t) op->nd_max = std::max(op->nd_max, pd.tb_nd[t]);
+        for (int p = 0; p < pd.nprod; ++p) {
+            const int b1 = pd.pr_bra[p], b2 = pd.pr_ket[p], t = pd.pr_table[p];
+            if (b1 < 0 || b1 >= d->nblocks || b2 < 0 || b2 >= d->nblocks || t < 0 || t >= pd.ntables) {
+                set_error("product references a block or table out of range");
+                return RMB_ERR_INVALID;
+            }
+            if (pd.tb_dm1[t] != d->blk_dm[b1] || pd.tb_dm2[t] != d->blk_dm[b2]) {
+                set_error("M table shape does not match the (J,sym) block dim_m");
+                return RMB_ERR_INVALID;
+            }
+            if (pd.pr_koff[p] < 0 ||
+                pd.pr_koff[p] + (long long)d->blk_dk[b1] * d->blk_dk[b2] > pd.kpool_len) {
+                set_error("K block out of range of kpool");
+                return RMB_ERR_INVALID;
+            }
+            hp.push_back({b1, b2, kbase + pd.pr_koff[p], ph.ent_begin + pd.tb_off[t], pd.tb_nd[t]});
+        }
+        for (long long e = 0; e < nent; ++e) {
+            // column bounds are checked per table below
+            (void)e;
+        }
+        for (int t = 0; t < pd.ntables; ++t)
+            for (long long e = pd.tb_off[t]; e < pd.tb_off[t + 1]; ++e)
+                if (pd.ent_col[e] >= pd.tb_dm2[t]) {
+                    set_error("M table column index out of range");
+                    return RMB_ERR_INVALID;
+                }
+        int rc = upload(&ph.d_coef, reinterpret_cast<const cplx*>(pd.ent_coef), (size_t)pd.ncart * nent);
+        if (rc) return rc;
+        rc = upload<double>(&ph.d_fprod, nullptr, (size_t)std::max(pd.ncart, 1));
+        if (rc) return rc;
+    }
+    op->nent = (long long)ent_col.size();
+    op->nprod = (int)hp.size();
+    // ---- sort products by bra block (stable: keeps part / input order inside a block)
+    std::vector<int> perm(hp.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return hp[a].bra < hp[b].bra; });
+    op->h_prods.resize(hp.size());
+    std::vector<int> bra_begin(d->nblocks + 1, 0);
+    for (size_t i = 0; i < perm.size(); ++i) {
+        const HProd& h = hp[perm[i]];
+        ProdD& pr = op->h_prods[i];
+        pr.ket_off = d->blk_off[h.ket];
+        pr.koff = h.koff;
+        pr.ent_off = h.ent_off;
+        pr.dk2 = d->blk_dk[h.ket];
+        pr.dm2 = d->blk_dm[h.ket];
+        pr.nd = h.nd;
+        pr.pad = 0;
+        bra_begin[h.bra + 1]++;
+    }
+    for (int b = 0; b < d->nblocks; ++b) bra_begin[b + 1] += bra_begin[b];
+    // ---- work items: row/column tiles of every bra block (also blocks without products: zeros)
+    const int S = 4;
+    op->matvec_S = S;
+    const int max_out = MV_THREADS * MV_ACC / S;   // outputs per state and CTA
+    int zstride = 1;
+    double flops = 0, opbytes = 0;
+    for (int b = 0; b < d->nblocks; ++b) {
+        const int dk1 = d->blk_dk[b], dm1 = d->blk_dm[b];
+        if (dk1 == 0 || dm1 == 0) continue;
+        int dk2max = 1;
+        for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
+            const ProdD& pr = op->h_prods[p];
+            dk2max = std::max(dk2max, pr.dk2);
+            // algorithmic work: K contraction + banded M contraction
+            flops += (kc ? 8.0 : 4.0) * dm1 * (double)dk1 * pr.dk2 + 8.0 * (double)pr.nd * dm1 * pr.dk2;
+            opbytes += (kc ? 16.0 : 8.0) * dk1 * pr.dk2;
+        }
+        const int ncols_t = std::min(dk1, max_out);
+        int nrows_t = std::max(1, std::min(dm1, max_out / ncols_t));
+        nrows_t = std::max(1, std::min(nrows_t, 1536 / dk2max));
+        if ((long long)dk2max * S * 16 > 160 * 1024) {
+            set_error("dim_k too large for the shared-memory tile of the matvec kernel");
+            return RMB_ERR_INVALID;
+        }
+        for (int c0 = 0; c0 < dk1; c0 += ncols_t)
+            for (int r0 = 0; r0 < dm1; r0 += nrows_t) {
+                ItemD it;
+                it.bra_off = d->blk_off[b];
+                it.dk1 = dk1;
+                it.r0 = r0;
+                it.nrows = std::min(nrows_t, dm1 - r0);
+                it.c0 = c0;
+                it.ncols = std::min(ncols_t, dk1 - c0);
+                it.p_begin = bra_begin[b];
+                it.p_end = bra_begin[b + 1];
+                it.dk2max = dk2max;
+                op->h_items.push_back(it);
+                zstride = std::max(zstride, it.nrows * dk2max);
+            }
+    }
+    opbytes += 20.0 * (double)op->nent;   // MF values + column indices
+    op->flops_per_state = flops;
+    op->op_bytes = opbytes;
+    // heaviest items first (tail balance)
+    std::stable_sort(op->h_items.begin(), op->h_items.end(), [&](const ItemD& a, const ItemD& b) {
+        auto cost = [&](const ItemD& it) {
+            double c = 0;
+            for (int p = it.p_begin; p < it.p_end; ++p)
+                c += (double)it.nrows * op->h_prods[p].dk2 * (it.ncols + 2.0 * op->h_prods[p].nd);
+            return c;
+        };
+        return cost(a) > cost(b);
+    });
+    op->nitems = (int)op->h_items.size();
+    op->matvec_smem = (size_t)S * zstride * sizeof(cplx);
+    int rc;
+    if ((rc = upload(&op->d_prods, op->h_prods.data(), op->h_prods.size()))) return rc;
+    if ((rc = upload(&op->d_items, op->h_items.data(), op->h_items.size()))) return rc;
+    if ((rc = upload(&op->d_ent_col, ent_col.data(), ent_col.size()))) return rc;
+    if ((rc = upload<cplx>(&op->d_ent_val, nullptr, (size_t)op->nent))) return rc;
+    RMB_CUDA(cudaMemset(op->d_ent_val, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
+    if ((rc = upload(&op->d_kpool, kpool.data(), kpool.size()))) return rc;
+    if ((rc = upload<int>(&op->d_flags, nullptr, (size_t)d->nparts + 1))) return rc;
+    RMB_CUDA(cudaMemset(op->d_flags, 0, ((size_t)d->nparts + 1) * sizeof(int)));
+    if (op->matvec_smem > 48 * 1024) {
+        RMB_CUDA(cudaFuncSetAttribute(k_matvec_scalar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)op->matvec_smem));
+        RMB_CUDA(cudaFuncSetAttribute(k_matvec_scalar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)op->matvec_smem));
+    }
+    guard.p = nullptr;
+    *out = op;
+    return RMB_OK;
+}
+
+int64_t rmb_operator_dim(const rmb_operator* op) { return op ? op->n : 0; }
+
+int64_t rmb_operator_nentries(const rmb_operator* op, int32_t part) {
+    if (!op || part < 0 || part >= (int)op->parts.size()) return -1;
+    return op->parts[part].ent_end - op->parts[part].ent_begin;
+}
+
+int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fprod, double thresh,
+                               int32_t all_dropped, void* stream) {
+    if (!op || part < 0 || part >= (int)op->parts.size() || !fprod) {
+        set_error("set_field: bad operator part");
+        return RMB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PartH& ph = op->parts[part];
+    RMB_CUDA(cudaMemcpyAsync(ph.d_fprod, fprod, sizeof(double) * ph.ncart, cudaMemcpyHostToDevice, st));
+    const long long nent = ph.ent_end - ph.ent_begin;
+    RMB_CUDA(cudaMemsetAsync(op->d_flags + 1 + part, 0, sizeof(int), st));
+    if (nent > 0) {
+        const int nt = 256;
+        k_field_contract<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
+            nent, ph.ncart, ph.d_coef, ph.d_fprod, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
+            op->d_flags + 1 + part);
+        RMB_CUDA(cudaGetLastError());
+        op->n_launches++;
+    }
+    ph.has_field = true;
+    ph.all_dropped = all_dropped != 0;
+    return RMB_OK;
+}
+
+int32_t rmb_operator_get_mf(rmb_operator* op, int32_t part, double* out_host, void* stream) {
+    if (!op || part < 0 || part >= (int)op->parts.size() || !out_host) {
+        set_error("get_mf: bad operator part");
+        return RMB_ERR_INVALID;
+    }
+    PartH& ph = op->parts[part];
+    if (!ph.has_field) {
+        set_error("operator part has no field applied");
+        return RMB_ERR_NOFIELD;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RMB_CUDA(cudaMemcpyAsync(out_host, op->d_ent_val + ph.ent_begin,
+                             sizeof(cplx) * (ph.ent_end - ph.ent_begin), cudaMemcpyDeviceToHost, st));
+    RMB_CUDA(cudaStreamSynchronize(st));
+    return RMB_OK;
+}
+
+int32_t rmb_operator_mf_nonempty(rmb_operator* op, void* stream) {
+    if (!op) return RMB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int> flags(op->parts.size() + 1, 0);
+    RMB_CUDA(cudaMemcpyAsync(flags.data(), op->d_flags, sizeof(int) * flags.size(), cudaMemcpyDeviceToHost, st));
+    RMB_CUDA(cudaStreamSynchronize(st));
+    for (size_t q = 0; q < op->parts.size(); ++q)
+        if (op->parts[q].has_field && flags[1 + q]) return 1;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace rmb {
+
+static int check_field(rmb_operator* op) {
+    for (auto& p : op->parts)
+        if (!p.has_field) {
+            set_error("you need to multiply tensor with field before applying it to a vector");
+            return RMB_ERR_NOFIELD;
+        }
+    return RMB_OK;
+}
+
+static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
+                         long long ldy, const int* active, cudaStream_t st) {
+    if (op->nitems == 0 || nstates == 0) return RMB_OK;
+    const int S = op->matvec_S;
+    const int zstride = (int)(op->matvec_smem / (S * sizeof(cplx)));
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (op->time_matvec) {
+        if (!op->mv_event_pool.empty()) {
+            ev = op->mv_event_pool.back();
+            op->mv_event_pool.pop_back();
+        } else {
+            RMB_CUDA(cudaEventCreate(&ev.first));
+            RMB_CUDA(cudaEventCreate(&ev.second));
+        }
+        RMB_CUDA(cudaEventRecord(ev.first, st));
+    }
+    // grid.y is limited to 65535: loop over slices of states
+    const long long max_y = 65535;
+    for (long long s0 = 0; s0 < nstates; s0 += max_y * S) {
+        const long long ns = std::min(nstates - s0, max_y * S);
+        dim3 grid((unsigned)op->nitems, (unsigned)((ns + S - 1) / S));
+        if (op->k_complex)
+            k_matvec_scalar<true><<<grid, MV_THREADS, op->matvec_smem, st>>>(
+                op->d_items, op->d_prods, op->d_ent_col, op->d_ent_val, op->d_kpool, X + s0 * ldx,
+                Y + s0 * ldy, ldx, ldy, (int)ns, S, active ? active + s0 : nullptr, zstride);
+        else
+            k_matvec_scalar<false><<<grid, MV_THREADS, op->matvec_smem, st>>>(
+                op->d_items, op->d_prods, op->d_ent_col, op->d_ent_val, op->d_kpool, X + s0 * ldx,
+                Y + s0 * ldy, ldx, ldy, (int)ns, S, active ? active + s0 : nullptr, zstride);
+        op->n_launches++;
+    }
+    RMB_CUDA(cudaGetLastError());
+    if (op->time_matvec) {
+        RMB_CUDA(cudaEventRecord(ev.second, st));
+        op->mv_events.push_back(ev);
+    }
+    op->n_matvec_launches++;
+    return RMB_OK;
+}
+
+template <typename T>
+static int ensure(T** p, size_t count) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    RMB_CUDA(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return RMB_OK;
+}
+
+// (re)allocate the per-state small arrays and the w / W vectors for `cap` states
+static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
+    if (cap <= op->ws_states && maxorder <= op->ws_maxorder && op->d_w) return RMB_OK;
+    cap = std::max(cap, op->ws_states);
+    maxorder = std::max(maxorder, op->ws_maxorder);
+    RMB_CUDA(cudaDeviceSynchronize());
+    for (auto* s : op->slabs) cudaFree(s);
+    op->slabs.clear();
+    op->slab_ptrs_uploaded = 0;
+    op->nchunk = nchunks(op->n);
+    int rc;
+    const size_t vec = (size_t)cap * (size_t)op->n;
+    if ((rc = ensure(&op->d_w, vec))) return rc;
+    if ((rc = ensure(&op->d_W, vec))) return rc;
+    if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->d_beta, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->d_ccur, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->d_dc, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->d_active, (size_t)cap))) return rc;
+    if ((rc = ensure(&op->d_order, (size_t)cap))) return rc;
+    if ((rc = ensure(&op->d_pdot, (size_t)cap * op->nchunk))) return rc;
+    if ((rc = ensure(&op->d_pnrm, (size_t)cap * op->nchunk))) return rc;
+    if ((rc = ensure(&op->d_pconv, (size_t)cap * op->nchunk))) return rc;
+    if (!op->d_ctrl) {
+        if ((rc = ensure(&op->d_ctrl, 4))) return rc;
+        RMB_CUDA(cudaMallocHost((void**)&op->h_ctrl, 4 * sizeof(int)));
+    }
+    op->ws_states = cap;
+    op->ws_maxorder = maxorder;
+    return RMB_OK;
+}
+
+static int ensure_slab(rmb_operator* op, int k, cudaStream_t st) {
+    while ((int)op->slabs.size() <= k) {
+        cplx* p = nullptr;
+        RMB_CUDA(cudaMalloc((void**)&p, (size_t)op->ws_states * (size_t)op->n * sizeof(cplx)));
+        op->slabs.push_back(p);
+    }
+    if (op->slab_ptrs_cap < (int)op->slabs.size() || !op->d_slab_ptrs) {
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if (op->d_slab_ptrs) cudaFree(op->d_slab_ptrs);
+        op->slab_ptrs_cap = std::max(16, (int)op->slabs.size() * 2);
+        op->slab_ptrs_uploaded = 0;
+        RMB_CUDA(cudaMalloc((void**)&op->d_slab_ptrs, op->slab_ptrs_cap * sizeof(cplx*)));
+    }
+    if (op->slab_ptrs_uploaded != (int)op->slabs.size()) {
+        RMB_CUDA(cudaMemcpyAsync(op->d_slab_ptrs, op->slabs.data(), op->slabs.size() * sizeof(cplx*),
+                                 cudaMemcpyHostToDevice, st));
+        op->slab_ptrs_uploaded = (int)op->slabs.size();
+    }
+    return RMB_OK;
+}
+
+// One sub-batch of states through the literal Lanczos loop of tdse.py:417-486.
+static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol,
+                         int maxorder, const cplx* ph, int* orders_host, cudaStream_t st,
+                         bool* hit_maxorder) {
+    const long long n = op->n;
+    const int nch = op->nchunk;
+    const dim3 vgrid((unsigned)nch, (unsigned)B);
+    const int ts = op->ws_maxorder, bs = op->ws_maxorder + 1;
+    int rc;
+    if ((rc = ensure_slab(op, 1, st))) return rc;
+    k_fill_int<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, 1, (int)B);
+    k_fill_int<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_order, 0, (int)B);
+    k_phase_init<<<vgrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], n, n);
+    op->n_launches += 3;
+    long long n_active = B;
+    int k = 0;
+    for (;; ++k) {
+        if ((rc = ensure_slab(op, k + 1, st))) return rc;
+        cplx* Vk = op->slabs[k];
+        if (k > 0) {
+            // V_k = W_{k-1} / beta_k  (or the Gram-Schmidt fallback when beta_k == 0)
+            k_scale<<<vgrid, VEC_THREADS, 0, st>>>(op->d_W, Vk, n, n, op->d_beta, bs, k, op->d_active);
+            op->n_launches++;
+            if (op->h_ctrl[2] > 0) {
+                k_fallback_ones<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_beta, bs, k,
+                                                                     op->d_active);
+                op->n_launches++;
+            }
+        }
+        if ((rc = launch_matvec(op, Vk, op->d_w, B, n, n, op->d_active, st))) return rc;
+        op->n_state_matvecs += n_active;
+        k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, n, n, op->d_pdot, nch, op->d_active);
+        k_recur<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, k > 0 ? op->slabs[k - 1] : nullptr, op->d_W, n, n,
+                                               op->d_pdot, nch, op->d_alpha, op->d_beta, ts, bs, k,
+                                               op->d_pnrm, op->d_active);
+        k_small<<<(unsigned)B, 32, 0, st>>>(op->d_pnrm, nch, op->d_alpha, op->d_beta, ts, bs, k, fac,
+                                            op->d_ccur, op->d_dc, op->d_active);
+        op->n_launches += 3;
+        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, 4 * sizeof(int), st));
+        if (k > 0) {
+            k_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_dc, ts, k, op->d_pconv, nch,
+                                                  op->d_active);
+            k_decide<<<(unsigned)B, 32, 0, st>>>(op->d_pconv, nch, tol, k, maxorder, op->d_active,
+                                                 op->d_order, op->d_ctrl);
+            op->n_launches += 2;
+        }
+        k_count_zero_beta<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_beta, bs, k + 1, op->d_active,
+                                                                        (int)B, op->d_ctrl);
+        op->n_launches++;
+        op->n_iterations++;
+        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if (k > 0) n_active = op->h_ctrl[0];
+        if (op->h_ctrl[1]) *hit_maxorder = true;
+        if (k > 0 && n_active == 0) break;
+        if (k == 0 && maxorder <= 1) {   // `while k < maxorder` never entered (tdse.py:450,480)
+            *hit_maxorder = true;
+            break;
+        }
+    }
+    k_combine<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_ccur, ts, op->d_order, ph, psi, ld);
+    op->n_launches++;
+    RMB_CUDA(cudaGetLastError());
+    if (orders_host) {
+        RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaStreamSynchronize(st));
+    }
+    return RMB_OK;
+}
+
+static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long long ld, cplx fac,
+                            double tol, int maxorder, const cplx* ph, int skip, int* orders_host,
+                            cudaStream_t st) {
+    const long long n = op->n;
+    if (nstates == 0) return RMB_OK;
+    if (skip) {
+        if (ph) {
+            const long long max_y = 65535;
+            for (long long s0 = 0; s0 < nstates; s0 += max_y) {
+                const long long ns = std::min(nstates - s0, max_y);
+                k_phase_mul2<<<dim3((unsigned)nchunks(n), (unsigned)ns), VEC_THREADS, 0, st>>>(psi + s0 * ld, ld, ph, n);
+                op->n_launches++;
+            }
+            RMB_CUDA(cudaGetLastError());
+        }
+        if (orders_host) std::fill(orders_host, orders_host + nstates, 0);
+        return RMB_OK;
+    }
+    int rc = check_field(op);
+    if (rc) return rc;
+    if (maxorder < 1 || maxorder > MAX_ORDER_SMEM) {
+        set_error("maxorder must be in [1, 128]");
+        return RMB_ERR_INVALID;
+    }
+    // sub-batch size from the workspace budget: w, W and ~14 Krylov vectors per state
+    long long budget = op->ws_budget;
+    if (budget <= 0) {
+        size_t fr = 0, tot = 0;
+        RMB_CUDA(cudaMemGetInfo(&fr, &tot));
+        long long held = (long long)(op->slabs.size() + 2) * op->ws_states * n * (long long)sizeof(cplx);
+        budget = (long long)(0.4 * (double)(fr + (size_t)held));
+    }
+    long long per_state = 16LL * n * (long long)sizeof(cplx);
+    long long bc = std::max(1LL, std::min({nstates, budget / per_state, 65535LL}));
+    if ((rc = ensure_workspace(op, bc, maxorder))) return rc;
+    bool hit = false;
+    for (long long s0 = 0; s0 < nstates; s0 += bc) {
+        const long long b = std::min(bc, nstates - s0);
+        rc = lanczos_batch(op, psi + s0 * ld, b, ld, fac, tol, maxorder, ph,
+                           orders_host ? orders_host + s0 : nullptr, st, &hit);
+        if (rc) return rc;
+    }
+    if (hit) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
+        set_error(buf);
+        return RMB_ERR_MAXORDER;
+    }
+    return RMB_OK;
+}
+
+}  // namespace rmb
+
+extern "C" {
+
+int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t nstates, int64_t ld,
+                   void* stream) {
+    if (!op || !x_dev || !y_dev || x_dev == y_dev || ld < op->n) {
+        set_error("matvec: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    int rc = check_field(op);
+    if (rc) return rc;
+    rc = launch_matvec(op, (const cplx*)x_dev, (cplx*)y_dev, nstates, ld, ld, nullptr, (cudaStream_t)stream);
+    if (rc == RMB_OK) op->n_state_matvecs += nstates;
+    return rc;
+}
+
+int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld, double fac_re,
+                           double fac_im, double tol, int32_t maxorder, const double* h0phase_dev,
+                           int32_t skip_krylov, int32_t* orders_host, void* stream) {
+    if (!op || !psi_dev || ld < op->n || nstates < 0) {
+        set_error("propagate_step: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    return propagate_device(op, (cplx*)psi_dev, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder,
+                            (const cplx*)h0phase_dev, skip_krylov, orders_host, (cudaStream_t)stream);
+}
+
+int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
+                                int64_t nstates, int64_t ld, double fac_re, double fac_im, double tol,
+                                int32_t maxorder, const double* h0phase_host, int32_t skip_krylov,
+                                int32_t* orders_host, void* stream) {
+    if (!op || !psi_in_host || !psi_out_host || ld < op->n || nstates < 0) {
+        set_error("propagate_step_host: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long elems = (long long)nstates * ld;
+    if (elems > op->stage_elems) {
+        RMB_CUDA(cudaStreamSynchronize(st));
+        int rc = ensure(&op->d_stage, (size_t)elems);
+        if (rc) return rc;
+        op->stage_elems = elems;
+    }
+    const cplx* ph = nullptr;
+    if (h0phase_host) {
+        if (op->n > op->phase_elems) {
+            int rc = ensure(&op->d_phase, (size_t)op->n);
+            if (rc) return rc;
+            op->phase_elems = op->n;
+        }
+        RMB_CUDA(cudaMemcpyAsync(op->d_phase, h0phase_host, sizeof(cplx) * op->n, cudaMemcpyHostToDevice, st));
+        ph = op->d_phase;
+    }
+    RMB_CUDA(cudaMemcpyAsync(op->d_stage, psi_in_host, sizeof(cplx) * elems, cudaMemcpyHostToDevice, st));
+    int rc = propagate_device(op, op->d_stage, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder, ph,
+                              skip_krylov, orders_host, st);
+    if (rc != RMB_OK && rc != RMB_ERR_MAXORDER) return rc;
+    RMB_CUDA(cudaMemcpyAsync(psi_out_host, op->d_stage, sizeof(cplx) * elems, cudaMemcpyDeviceToHost, st));
+    RMB_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates, int64_t ld,
+                        double* expval_dev, void* stream) {
+    if (!op || !psi_dev || !expval_dev || ld < op->n) {
+        set_error("expectation: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    int rc = check_field(op);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = op->n;
+    if (nstates == 0) return RMB_OK;
+    if (op->ws_states == 0) {
+        // product vector only: at most 1 GiB of scratch
+        const long long cap = std::max<long long>(1, (1LL << 30) / (n * (long long)sizeof(cplx)));
+        if ((rc = ensure_workspace(op, std::min<long long>({(long long)nstates, cap, 65535LL}), 1))) return rc;
+    }
+    const long long bc = op->ws_states;
+    const int nch = op->nchunk;
+    for (long long s0 = 0; s0 < nstates; s0 += bc) {
+        const long long b = std::min(bc, (long long)nstates - s0);
+        const cplx* psi = (const cplx*)psi_dev + s0 * ld;
+        if ((rc = launch_matvec(op, psi, op->d_w, b, ld, n, nullptr, st))) return rc;
+        k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(psi, ld, op->d_w, n, n, op->d_pdot, nch);
+        k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, nch, (cplx*)expval_dev + s0);
+        op->n_launches += 2;
+        op->n_state_matvecs += b;
+    }
+    RMB_CUDA(cudaGetLastError());
+    return RMB_OK;
+}
+
+int32_t rmb_populations(const double* psi_dev, int64_t nstates, int64_t n, int64_t ld, double* pop_dev,
+                        void* stream) {
+    if (!psi_dev || !pop_dev || ld < n) {
+        set_error("populations: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    if (n == 0) return RMB_OK;
+    k_populations<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const cplx*)psi_dev, nstates, n, ld, pop_dev);
+    RMB_CUDA(cudaGetLastError());
+    return RMB_OK;
+}
+
+int32_t rmb_set_workspace_budget(rmb_operator* op, int64_t bytes) {
+    if (!op) return RMB_ERR_INVALID;
+    op->ws_budget = bytes;
+    return RMB_OK;
+}
+
+int32_t rmb_get_counters(const rmb_operator* op, int64_t* out4) {
+    if (!op || !out4) return RMB_ERR_INVALID;
+    out4[0] = op->n_launches;
+    out4[1] = op->n_matvec_launches;
+    out4[2] = op->n_iterations;
+    out4[3] = op->n_state_matvecs;
+    return RMB_OK;
+}
+
+int32_t rmb_matvec_timing(rmb_operator* op, int32_t enable, double* ms_out, int64_t* launches_out) {
+    if (!op) return RMB_ERR_INVALID;
+    double ms = 0;
+    long long cnt = 0;
+    for (auto& e : op->mv_events) {
+        RMB_CUDA(cudaEventSynchronize(e.second));
+        float t = 0;
+        RMB_CUDA(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+        cnt++;
+        op->mv_event_pool.push_back(e);
+    }
+    op->mv_events.clear();
+    if (ms_out) *ms_out = ms;
+    if (launches_out) *launches_out = cnt;
+    op->time_matvec = enable != 0;
+    return RMB_OK;
+}
+
+}  // extern "C"

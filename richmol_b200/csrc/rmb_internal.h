@@ -1,0 +1,116 @@
+// Internal declarations shared by the translation units of librichmol_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/richmol_b200.h"
+
+namespace rmb {
+
+typedef double2 cplx;
+
+// one (Jpair, sympair, irrep) block product, device layout
+struct ProdD {
+    long long ket_off;   // offset of the ket (J,sym) block in the flat state vector
+    long long koff;      // offset of the dk1 x dk2 K block in the K pool (elements)
+    long long ent_off;   // offset of the MF table (row 0) in the global entry pool
+    int dk2;             // ket dim_k
+    int dm2;             // ket dim_m
+    int nd;              // ELL width of the MF table
+    int pad;
+};
+
+// one work item of the matvec: a tile of rows (m1) x columns (k1) of one bra block
+struct ItemD {
+    long long bra_off;   // offset of the bra block in the flat state vector
+    int dk1;             // bra dim_k
+    int r0, nrows;       // m1 tile
+    int c0, ncols;       // k1 tile
+    int p_begin, p_end;  // products with this bra block (sorted by bra)
+    int dk2max;          // max ket dim_k over those products
+};
+
+struct PartH {
+    int ncart = 0;
+    long long ent_begin = 0, ent_end = 0;   // range in the global entry pool
+    cplx* d_coef = nullptr;                 // [ncart][nent]
+    double* d_fprod = nullptr;              // [ncart]
+    bool has_field = false;
+    bool all_dropped = false;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RMB_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return rmb::cuda_fail(e__, #call); \
+    } while (0)
+
+}  // namespace rmb
+
+struct rmb_operator {
+    int device = 0;
+    int num_sms = 148;
+    long long n = 0;                 // Hilbert-space dimension
+    int nblocks = 0;
+    int nprod = 0;
+    int nitems = 0;
+    bool k_complex = false;
+    int dk_max = 1;                  // max dim_k over blocks
+    int nd_max = 1;
+    long long nent = 0;
+    // device tables
+    rmb::ProdD* d_prods = nullptr;
+    rmb::ItemD* d_items = nullptr;
+    int* d_ent_col = nullptr;
+    rmb::cplx* d_ent_val = nullptr;
+    double* d_kpool = nullptr;       // doubles, or interleaved complex if k_complex
+    int* d_flags = nullptr;          // [0] mf non-empty flag (per set_field accumulates), [1..] scratch
+    std::vector<rmb::PartH> parts;
+    std::vector<rmb::ItemD> h_items;
+    std::vector<rmb::ProdD> h_prods;
+    size_t matvec_smem = 0;          // dynamic shared memory of the matvec launch
+    int matvec_S = 1;                // states per CTA
+    // algorithmic work per state-matvec (for DESIGN.md / bench roofline)
+    double flops_per_state = 0;
+    double op_bytes = 0;
+
+    // ---- Krylov workspace (lazily sized) ----
+    long long ws_budget = 0;         // bytes; 0 = auto
+    long long ws_states = 0;         // capacity in states of each slab
+    std::vector<rmb::cplx*> slabs;   // V_0, V_1, ... each ws_states * n
+    rmb::cplx* d_w = nullptr;        // H V_k
+    rmb::cplx* d_W = nullptr;        // residual W_k
+    rmb::cplx** d_slab_ptrs = nullptr;   // device copy of slab pointers
+    int slab_ptrs_cap = 0;
+    int slab_ptrs_uploaded = 0;
+    // per-state small arrays (capacity ws_states, order capacity ws_maxorder)
+    int ws_maxorder = 0;
+    rmb::cplx* d_alpha = nullptr;    // [S][maxorder]
+    double* d_beta = nullptr;        // [S][maxorder+1]
+    rmb::cplx* d_ccur = nullptr;     // [S][maxorder]
+    rmb::cplx* d_dc = nullptr;       // [S][maxorder]
+    int* d_active = nullptr;         // [S]
+    int* d_order = nullptr;          // [S]
+    rmb::cplx* d_pdot = nullptr;     // [S][nchunk]
+    double* d_pnrm = nullptr;        // [S][nchunk]
+    double* d_pconv = nullptr;       // [S][nchunk]
+    int* d_ctrl = nullptr;           // [0] n_active, [1] maxorder flag, [2] n_zero_beta
+    int* h_ctrl = nullptr;           // pinned mirror
+    int nchunk = 0;
+    // host staging for the *_host entry point
+    rmb::cplx* d_stage = nullptr;
+    long long stage_elems = 0;
+    rmb::cplx* d_phase = nullptr;
+    long long phase_elems = 0;
+
+    // counters
+    long long n_launches = 0, n_matvec_launches = 0, n_iterations = 0, n_state_matvecs = 0;
+    bool time_matvec = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> mv_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> mv_event_pool;
+};

@@ -1,0 +1,112 @@
+"""Pins the CPU oracle (oracle/port.py) against the golden vectors generated from the UNMODIFIED
+reference (tests/golden/make_golden.py) and, when /root/reference is present, against the live
+reference itself."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port, refshim
+
+from helpers import AUPOL, DEBYE, EXP_FAC, golden, load, oracle_of, relerr
+
+
+def test_g1_reference_unit_test_populations():
+    """tests/test_tdse.py:15-110 of the reference: OCS, J even, m = 0, 500 steps."""
+    g = golden("g1_ocs_run.npz")
+    h0, al = oracle_of(load("g1_ocs_h0.npz")), oracle_of(load("g1_ocs_alpha.npz"))
+    al.mul(-0.5)
+    al.mul(AUPOL)
+    vecs = port.init_state(h0, temp=0)
+    phase = port.h0_phase(h0, EXP_FAC)
+    k, orders = 0, []
+    for i, E in enumerate(g["field"]):
+        al.field(E)
+        o = []
+        vecs = port.update_step(al, vecs, EXP_FAC, phase=phase, orders=o)
+        orders.append(o)
+        if i % 10 == 0:
+            assert relerr(vecs, g["raw"][k]) < 1e-12
+            pops = np.abs(vecs[0][:7]) ** 2
+            # the reference's own output file, 4 decimals
+            assert np.max(np.abs(np.round(pops, 4) - g["pop_lanczos"][k, 1:])) <= 1.0001e-4
+            k += 1
+    assert np.array_equal(np.array(orders), g["orders"])
+    assert relerr(vecs, g["final"]) < 1e-12
+
+
+def test_g2_thermal_ensemble_with_thresholds():
+    g = golden("g2_ocs_run.npz")
+    h0, al = oracle_of(load("g2_ocs_h0.npz")), oracle_of(load("g2_ocs_alpha.npz"))
+    al.mul(-0.5)
+    al.mul(AUPOL)
+    vecs = port.init_state(h0, temp=1.0)
+    assert relerr(vecs, g["vecs0"]) < 1e-15
+    phase = port.h0_phase(h0, EXP_FAC)
+    for i, E in enumerate(g["fields"]):
+        al.field(E, thresh=float(g["thresh"]))
+        o = []
+        vecs = port.update_step(al, vecs, EXP_FAC, phase=phase, orders=o)
+        assert relerr(vecs, g["outs"][i]) < 1e-12
+        assert o == list(g["orders"][i])
+        y = port.flat_matvec(al, g["x"]) if al.mfmat else np.zeros_like(g["x"])
+        assert relerr(y, g["matvec"][i]) < 1e-14 or not np.any(g["matvec"][i])
+
+
+def test_g3_camphor_lazy_sum():
+    g = golden("g3_camphor_run.npz")
+    h0 = oracle_of(load("g3_camphor_h0.npz"))
+    mu, al = oracle_of(load("g3_camphor_mu.npz")), oracle_of(load("g3_camphor_alpha.npz"))
+    mu.mul(-1.0)
+    mu.mul(DEBYE)
+    al.mul(-0.5)
+    al.mul(AUPOL)
+    vecs = port.init_state(h0, temp=2.0)
+    assert relerr(vecs, g["vecs0"]) < 1e-15
+    phase = port.h0_phase(h0, EXP_FAC)
+    mu.field(g["dc"])
+    for i, E in enumerate(g["fields"]):
+        al.field(E, thresh=float(g["thresh"]))
+        H = mu.add(al)
+        o = []
+        if i % 2 == 0:
+            vecs = port.update_step(H, vecs, EXP_FAC, phase=phase, orders=o)
+        else:
+            vecs = port.update_step(H.add(h0), vecs, EXP_FAC, orders=o)
+        assert relerr(vecs, g["outs"][i]) < 1e-12
+        assert o == list(g["orders"][i])
+        assert relerr(port.flat_matvec(H, g["x"]), g["matvec"][i]) < 1e-14
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_port_against_live_reference():
+    r = refshim.load()
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        path = 'tests/benchmarks/data/r-camphor_rchm_files/'
+        filt = lambda **kw: kw.get('J', 0) <= 2
+        with contextlib.redirect_stdout(io.StringIO()):
+            mu = r.trove.CarTensTrove(path + 'camphor_energies_j0_j20.rchm',
+                                      path + 'camphor_matelem_mu_j<j1>_j<j2>.rchm', bra=filt, ket=filt)
+            h0 = r.trove.CarTensTrove(path + 'camphor_energies_j0_j20.rchm', bra=filt, ket=filt)
+    finally:
+        os.chdir(cwd)
+    mu.mul(-DEBYE)
+    om, oh = port.OracleTensor(mu), port.OracleTensor(h0)
+    tdse = r.tdse.TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    v_ref = tdse.init_state(h0, temp=5.0)
+    v_or = port.init_state(oh, temp=5.0)
+    assert relerr(v_or, v_ref) < 1e-15
+    phase = port.h0_phase(oh, EXP_FAC)
+    for E in ([1e7, 0, 0], [2e7, -1e7, 3e7], [0, 0, 5e7]):
+        mu.field(E)
+        om.field(E)
+        v_ref, _ = tdse.update(mu, v_ref, H0=h0)
+        v_or = port.update_step(om, v_or, EXP_FAC, phase=phase)
+        assert relerr(v_or, v_ref) < 1e-13
+    assert relerr(om.tomat().toarray(), mu.tomat(form='full', repres='dense')) < 1e-15
