@@ -205,6 +205,10 @@ class CarTens:
         for a in ("_packed", "_basis_cache", "_mfmat_cache"):
             self.__dict__.pop(a, None)
 
+    def _has_field(self):
+        """hasattr(self, 'mfmat') without touching the device."""
+        return all(fs is not None for _, fs, _ in self._parts())
+
     def _krylov_skippable(self):
         """True when `mfmat` is known to be empty without asking the device (every field product
         screened out; richmol/field.py:1107-1112 and richmol/tdse.py:377)."""

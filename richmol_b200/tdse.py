@@ -122,6 +122,7 @@ class TDSE():
             assert (temp >= 0), f"temperature `temp` has negative value: '{temp}'"
         assert (thresh >= 0), f"partition function threshold `thresh` has negative or zero value: '{thresh}'"
 
+        H = _as_cartens(H, self._cache)
         H_is_diag = False
         try:
             if H.cart[0] == "0":
@@ -130,10 +131,13 @@ class TDSE():
         except AttributeError:
             pass
 
-        if not hasattr(H, "mfmat"):
+        if not H._has_field():
             raise AttributeError("hamiltonian `H` has inappropriate type (must be Hamiltonian)") from None
         if H_is_diag:
-            enrs = H.tomat(form="full", repres="csr_matrix").diagonal()
+            # field([0,0,1]) on a rank-0 tensor gives MF = 1 * M['0'] (field.py:1099), so the
+            # potential equals the '0' component; taking it from the host tables keeps this
+            # set-up step independent of the device
+            enrs = H.tomat(form="full", repres="csr_matrix", cart="0").diagonal()
             vecs = diags(np.ones(len(enrs)), format='csr')
         else:
             hmat = H.tomat(form="full", repres="dense")
@@ -159,7 +163,10 @@ class TDSE():
             beta = 1.0 / (const.value("Boltzmann constant") * temp)
             weights = np.exp(-beta * enrs)
             weights /= np.sum(weights)
-            csum = np.cumsum(weights)
+            if len(weights) <= 20000:
+                csum = np.array([np.sum(weights[: i + 1]) for i in range(len(weights))])
+            else:
+                csum = np.cumsum(weights)
             inds = [i for i in range(len(weights)) if (1 - csum[i]) > thresh]
             sqrt_weights = np.sqrt(weights[inds])
             vecs = vecs[inds].multiply(sqrt_weights[:, None])
@@ -196,8 +203,8 @@ class TDSE():
 
         Kwargs: `H0` (field-free Hamiltonian -> split-operator step), `matvec_lib` (accepted,
         ignored: the CUDA path is the only one), `propag` ('internal'; 'external' is served by the
-        same Lanczos kernel), `tol` (default 1e-15), and the extension
-        `inplace` (CUDA tensors only)."""
+        same Lanczos kernel), `tol` (default 1e-15), and the extensions
+        `inplace` (CUDA tensors only) and `out` (numpy result buffer, e.g. pinned memory)."""
         import ctypes as C
 
         if 'H0' in kwargs:
@@ -234,7 +241,7 @@ class TDSE():
 
         # with H0 the Krylov part only runs if the tensor has a (non-empty) mfmat (tdse.py:377);
         # without H0 the reference needs mfmat and fails in CarTens.vec otherwise
-        has_field = all(fs is not None for _, fs, _ in H._parts())
+        has_field = H._has_field()
         if H0 is not None:
             phase = self._h0_phase(H0, exp_fac)
             skip = (not has_field) or H._krylov_skippable()
@@ -286,7 +293,12 @@ class TDSE():
         if vin.ndim != 2 or vin.shape[1] != N:
             raise ValueError(f"vecs must have shape (nstates, {N}), got {vin.shape}")
         nst = vin.shape[0]
-        vout = np.empty_like(vin)
+        vout = kwargs.get('out')
+        if vout is None:
+            vout = np.empty_like(vin)
+        elif (not isinstance(vout, np.ndarray) or vout.shape != vin.shape or vout.dtype != np.complex128
+              or not vout.flags.c_contiguous):
+            raise ValueError("`out` must be a C-contiguous complex128 array of the shape of `vecs`")
         orders = np.zeros(nst, dtype=np.int32)
         ph = np.ascontiguousarray(phase, dtype=np.complex128) if phase is not None else None
         status = lib.rmb_propagate_step_host(

@@ -219,13 +219,27 @@ def test_zero_beta_fallback_and_exact_eigenvector():
             assert tdse.last_orders[i] == ref_orders[i]
 
 
-def test_maxorder_raises_value_error():
-    m = synth.ocs(10)
+def test_high_order_and_maxorder():
+    """Strong field: ~60 Lanczos vectors still match the oracle; a stronger one hits maxorder and
+    raises ValueError like the reference (tdse.py:480-484)."""
+    m = synth.ocs(24)
     h0, pol = m["h0"], m["pol"] * (-0.5 * AUPOL)
-    tdse = TDSE(t_end=100, dt=50.0)            # huge step: Lanczos cannot converge in 100 vectors
+    tdse = TDSE(t_end=1, dt=0.01)
     tdse.time_grid()
-    pol.field([0, 0, 5e10])
-    vecs = tdse.init_state(h0, temp=0)
+    o, oh = oracle_of(pol), oracle_of(h0)
+    vecs = random_states(2, o.N, seed=1)
+    s = 5e10
+    E = [0.6 * s, 0.3 * s, s]
+    pol.field(E)
+    o.field(E)
+    orders = []
+    ref = port.update_step(o, vecs.copy(), EXP_FAC, phase=port.h0_phase(oh, EXP_FAC), orders=orders)
+    out, _ = tdse.update(pol, vecs, H0=h0)
+    assert min(orders) > 40
+    assert list(tdse.last_orders) == orders
+    assert relerr(out, ref) < TOL
+    s = 1e11
+    pol.field([0.6 * s, 0.3 * s, s])
     with pytest.raises(ValueError, match="maximum order"):
         tdse.update(pol, vecs, H0=h0)
 
