@@ -8,6 +8,7 @@
 #include <numeric>
 
 #include "rmb_kernels.cuh"
+#include "rmb_matvec.cuh"
 
 namespace rmb {
 
@@ -55,8 +56,15 @@ void rmb_operator_destroy(rmb_operator* op) {
     if (!op) return;
     cudaFree(op->d_prods);
     cudaFree(op->d_items);
+    cudaFree(op->d_items2);
+    cudaFree(op->d_xranges);
+    cudaFree(op->d_units);
     cudaFree(op->d_ent_col);
     cudaFree(op->d_ent_val);
+    cudaFree(op->d_ent_tab);
+    cudaFree(op->d_tab_off);
+    cudaFree(op->d_tab_nd);
+    cudaFree(op->d_tab_mask);
     cudaFree(op->d_kpool);
     cudaFree(op->d_flags);
     for (auto& p : op->parts) {
@@ -125,7 +133,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     op->k_complex = kc;
     std::vector<int> ent_col;
     std::vector<double> kpool;
-    struct HProd { int bra, ket; long long koff, ent_off; int nd; };
+    struct HProd { int bra, ket; long long koff, ent_off; int nd, tab; };
+    std::vector<int> ent_tab, tab_off, tab_nd;
     std::vector<HProd> hp;
     op->parts.resize(d->nparts);
     for (int q = 0; q < d->nparts; ++q) {
@@ -135,6 +144,13 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         const long long nent = pd.tb_off ? pd.tb_off[pd.ntables] : 0;
         ph.ent_begin = (long long)ent_col.size();
         ph.ent_end = ph.ent_begin + nent;
+        ph.tab_begin = (int)tab_off.size();
+        ph.tab_end = ph.tab_begin + pd.ntables;
+        for (int t = 0; t < pd.ntables; ++t) {
+            tab_off.push_back((int)(ph.ent_begin + pd.tb_off[t]));
+            tab_nd.push_back(pd.tb_nd[t]);
+            for (long long e = pd.tb_off[t]; e < pd.tb_off[t + 1]; ++e) ent_tab.push_back(ph.tab_begin + t);
+        }
         ent_col.insert(ent_col.end(), pd.ent_col, pd.ent_col + nent);
         const long long kbase = (long long)(kc ? kpool.size() / 2 : kpool.size());
         if (kc && !pd.k_is_complex) {
@@ -161,7 +177,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 set_error("K block out of range of kpool");
                 return RMB_ERR_INVALID;
             }
-            hp.push_back({b1, b2, kbase + pd.pr_koff[p], ph.ent_begin + pd.tb_off[t], pd.tb_nd[t]});
+            hp.push_back({b1, b2, kbase + pd.pr_koff[p], ph.ent_begin + pd.tb_off[t], pd.tb_nd[t], ph.tab_begin + t});
         }
         for (long long e = 0; e < nent; ++e) {
             // column bounds are checked per table below
@@ -195,7 +211,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         pr.dk2 = d->blk_dk[h.ket];
         pr.dm2 = d->blk_dm[h.ket];
         pr.nd = h.nd;
-        pr.pad = 0;
+        pr.tab = h.tab;
         bra_begin[h.bra + 1]++;
     }
     for (int b = 0; b < d->nblocks; ++b) bra_begin[b + 1] += bra_begin[b];
@@ -205,17 +221,91 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     const int max_out = MV_THREADS * MV_ACC / S;   // outputs per state and CTA
     int zstride = 1;
     double flops = 0, opbytes = 0;
+    const char* force = getenv("RMB_MATVEC");
+    const bool force_scalar = force && strcmp(force, "scalar") == 0;
+    std::vector<Item2D> items2;
+    std::vector<XRange> xranges;
+    const size_t smem_budget = 110 * 1024;   // two CTAs per SM
     for (int b = 0; b < d->nblocks; ++b) {
         const int dk1 = d->blk_dk[b], dm1 = d->blk_dm[b];
         if (dk1 == 0 || dm1 == 0) continue;
-        int dk2max = 1;
+        int dk2max = 1, ndmax = 1;
         for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
             const ProdD& pr = op->h_prods[p];
             dk2max = std::max(dk2max, pr.dk2);
+            ndmax = std::max(ndmax, pr.nd);
             // algorithmic work: K contraction + banded M contraction
             flops += (kc ? 8.0 : 4.0) * dm1 * (double)dk1 * pr.dk2 + 8.0 * (double)pr.nd * dm1 * pr.dk2;
             opbytes += (kc ? 16.0 : 8.0) * dk1 * pr.dk2;
         }
+        // ---- tiled kernel: row tiles (<= 128 rows, one thread per row and state pair) x column
+        //      chunks (<= 16); falls back to the scalar kernel when the tile does not fit
+        bool fast = !force_scalar && ndmax <= MV2_NDMAX;   // diagonal slots handled in registers
+        if (fast) {
+            int best_nt = 0, best_pairs = 0;
+            double best_util = -1;
+            const int nt0 = (dm1 + MV2_THREADS - 1) / MV2_THREADS;
+            for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
+                const int nr = (dm1 + nt - 1) / nt;
+                int pairs = std::min(16, MV2_THREADS / nr);
+                // shared memory: K^T of all products + two ket-row buffers
+                auto need = [&](int pr_) {
+                    size_t kt = 0, xb = 0;
+                    for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
+                        const ProdD& q = op->h_prods[p];
+                        const int nc0 = std::min(dk1, MV2_NCMAX);
+                        const int ncp = nc0 == 1 ? 1 : ((nc0 + 1) & ~1);
+                        kt += (size_t)q.dk2 * ncp * (kc ? 2 : 1) * 8;
+                        xb = std::max(xb, (size_t)2 * pr_ * std::min(q.dm2, nr + 2 * q.nd) * (q.dk2 | 1) * 16);
+                    }
+                    return kt + 2 * xb;
+                };
+                while (pairs > 1 && need(pairs) > smem_budget) --pairs;
+                if (need(pairs) > smem_budget) continue;
+                const double util = (double)nr * pairs / MV2_THREADS * ((double)dm1 / (nr * nt));
+                if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_pairs = pairs; }
+            }
+            if (best_nt == 0) fast = false;
+            if (fast) {
+                const int nr_t = (dm1 + best_nt - 1) / best_nt;
+                for (int c0 = 0; c0 < dk1; c0 += MV2_NCMAX)
+                    for (int r0 = 0; r0 < dm1; r0 += nr_t) {
+                        Item2D it;
+                        it.bra_off = d->blk_off[b];
+                        it.dk1 = dk1;
+                        it.r0 = r0;
+                        it.nrows = std::min(nr_t, dm1 - r0);
+                        it.c0 = c0;
+                        it.nc = std::min(MV2_NCMAX, dk1 - c0);
+                        it.p_begin = bra_begin[b];
+                        it.p_end = bra_begin[b + 1];
+                        it.pairs = best_pairs;
+                        it.xr_off = (int)xranges.size();
+                        const int ncp = it.nc == 1 ? 1 : ((it.nc + 1) & ~1);
+                        int ktd = 0;
+                        for (int p = it.p_begin; p < it.p_end; ++p) {
+                            const ProdD& q = op->h_prods[p];
+                            ktd += q.dk2 * ncp * (kc ? 2 : 1);
+                            int lo = q.dm2, hi = -1;
+                            for (int r = it.r0; r < it.r0 + it.nrows; ++r)
+                                for (int j = 0; j < q.nd; ++j) {
+                                    const int col = ent_col[q.ent_off + (long long)r * q.nd + j];
+                                    if (col >= 0) { lo = std::min(lo, col); hi = std::max(hi, col); }
+                                }
+                            XRange xr;
+                            xr.c_lo = hi < 0 ? 0 : lo;
+                            xr.nr = hi < 0 ? 0 : hi - lo + 1;
+                            xranges.push_back(xr);
+                            op->xbuf_elems = std::max(op->xbuf_elems, 2 * it.pairs * xr.nr * (q.dk2 | 1));
+                        }
+                        it.kt_total = ktd;
+                        op->kt_doubles = std::max(op->kt_doubles, (ktd + 1) & ~1);
+                        items2.push_back(it);
+                    }
+                continue;
+            }
+        }
+        // ---- scalar kernel items
         const int ncols_t = std::min(dk1, max_out);
         int nrows_t = std::max(1, std::min(dm1, max_out / ncols_t));
         nrows_t = std::max(1, std::min(nrows_t, 1536 / dk2max));
@@ -239,6 +329,24 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 zstride = std::max(zstride, it.nrows * dk2max);
             }
     }
+    // heaviest tiled items first
+    {
+        std::vector<int> order(items2.size());
+        std::iota(order.begin(), order.end(), 0);
+        auto cost2 = [&](const Item2D& it) {
+            double c = 0;
+            for (int p = it.p_begin; p < it.p_end; ++p)
+                c += (double)it.nrows * op->h_prods[p].dk2 * (it.nc + 2.0 * op->h_prods[p].nd);
+            return c;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost2(items2[a]) > cost2(items2[b]); });
+        std::vector<Item2D> sorted;
+        for (int i : order) sorted.push_back(items2[i]);
+        items2.swap(sorted);
+    }
+    op->nitems2 = (int)items2.size();
+    for (auto& it : items2) op->h_item2_states.push_back(2 * it.pairs);
+    op->matvec2_smem = (size_t)op->kt_doubles * 8 + (size_t)2 * op->xbuf_elems * 16;
     opbytes += 20.0 * (double)op->nent;   // MF values + column indices
     op->flops_per_state = flops;
     op->op_bytes = opbytes;
@@ -257,17 +365,36 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     int rc;
     if ((rc = upload(&op->d_prods, op->h_prods.data(), op->h_prods.size()))) return rc;
     if ((rc = upload(&op->d_items, op->h_items.data(), op->h_items.size()))) return rc;
+    if ((rc = upload((Item2D**)&op->d_items2, items2.data(), items2.size()))) return rc;
+    if ((rc = upload((XRange**)&op->d_xranges, xranges.data(), xranges.size()))) return rc;
+    // the opt-in limit is a per-function, process-wide attribute: only ever raise it
+    static size_t g_tiled_smem = 48 * 1024;
+    if (op->matvec2_smem > g_tiled_smem) {
+        RMB_CUDA(cudaFuncSetAttribute(k_matvec_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)op->matvec2_smem));
+        RMB_CUDA(cudaFuncSetAttribute(k_matvec_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)op->matvec2_smem));
+        g_tiled_smem = op->matvec2_smem;
+    }
     if ((rc = upload(&op->d_ent_col, ent_col.data(), ent_col.size()))) return rc;
     if ((rc = upload<cplx>(&op->d_ent_val, nullptr, (size_t)op->nent))) return rc;
+    op->ntab = (int)tab_off.size();
+    if ((rc = upload(&op->d_ent_tab, ent_tab.data(), ent_tab.size()))) return rc;
+    if ((rc = upload(&op->d_tab_off, tab_off.data(), tab_off.size()))) return rc;
+    if ((rc = upload(&op->d_tab_nd, tab_nd.data(), tab_nd.size()))) return rc;
+    if ((rc = upload<unsigned>(&op->d_tab_mask, nullptr, tab_off.size()))) return rc;
+    RMB_CUDA(cudaMemset(op->d_tab_mask, 0, std::max<size_t>(1, tab_off.size()) * sizeof(unsigned)));
     RMB_CUDA(cudaMemset(op->d_ent_val, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
     if ((rc = upload(&op->d_kpool, kpool.data(), kpool.size()))) return rc;
     if ((rc = upload<int>(&op->d_flags, nullptr, (size_t)d->nparts + 1))) return rc;
     RMB_CUDA(cudaMemset(op->d_flags, 0, ((size_t)d->nparts + 1) * sizeof(int)));
-    if (op->matvec_smem > 48 * 1024) {
+    static size_t g_scalar_smem = 48 * 1024;
+    if (op->matvec_smem > g_scalar_smem) {
         RMB_CUDA(cudaFuncSetAttribute(k_matvec_scalar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)op->matvec_smem));
         RMB_CUDA(cudaFuncSetAttribute(k_matvec_scalar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)op->matvec_smem));
+        g_scalar_smem = op->matvec_smem;
     }
     guard.p = nullptr;
     *out = op;
@@ -292,11 +419,13 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
     RMB_CUDA(cudaMemcpyAsync(ph.d_fprod, fprod, sizeof(double) * ph.ncart, cudaMemcpyHostToDevice, st));
     const long long nent = ph.ent_end - ph.ent_begin;
     RMB_CUDA(cudaMemsetAsync(op->d_flags + 1 + part, 0, sizeof(int), st));
+    if (ph.tab_end > ph.tab_begin)
+        RMB_CUDA(cudaMemsetAsync(op->d_tab_mask + ph.tab_begin, 0, sizeof(unsigned) * (ph.tab_end - ph.tab_begin), st));
     if (nent > 0) {
         const int nt = 256;
         k_field_contract<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ncart, ph.d_coef, ph.d_fprod, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
-            op->d_flags + 1 + part);
+            op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, ph.ent_begin);
         RMB_CUDA(cudaGetLastError());
         op->n_launches++;
     }
@@ -348,7 +477,7 @@ static int check_field(rmb_operator* op) {
 
 static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
                          long long ldy, const int* active, cudaStream_t st) {
-    if (op->nitems == 0 || nstates == 0) return RMB_OK;
+    if ((op->nitems == 0 && op->nitems2 == 0) || nstates == 0) return RMB_OK;
     const int S = op->matvec_S;
     const int zstride = (int)(op->matvec_smem / (S * sizeof(cplx)));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -362,9 +491,39 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         }
         RMB_CUDA(cudaEventRecord(ev.first, st));
     }
+    if (op->nitems2 > 0) {
+        // work units (item, first state) for this batch size; rebuilt only when the size changes
+        if (op->units_nstates != nstates) {
+            std::vector<Unit2D> units;
+            for (int i = 0; i < op->nitems2; ++i)
+                for (long long s0 = 0; s0 < nstates; s0 += op->h_item2_states[i]) units.push_back({i, (int)s0});
+            if ((int)units.size() > op->units_cap) {
+                RMB_CUDA(cudaStreamSynchronize(st));
+                if (op->d_units) cudaFree(op->d_units);
+                op->units_cap = (int)units.size();
+                RMB_CUDA(cudaMalloc(&op->d_units, sizeof(Unit2D) * op->units_cap));
+            }
+            RMB_CUDA(cudaMemcpyAsync(op->d_units, units.data(), sizeof(Unit2D) * units.size(),
+                                     cudaMemcpyHostToDevice, st));
+            RMB_CUDA(cudaStreamSynchronize(st));   // `units` is pageable host memory
+            op->nunits = (int)units.size();
+            op->units_nstates = nstates;
+        }
+        if (op->k_complex)
+            k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
+                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
+                op->d_ent_col, op->d_ent_val, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                op->kt_doubles, op->xbuf_elems);
+        else
+            k_matvec_tiled<false><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
+                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
+                op->d_ent_col, op->d_ent_val, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                op->kt_doubles, op->xbuf_elems);
+        op->n_launches++;
+    }
     // grid.y is limited to 65535: loop over slices of states
     const long long max_y = 65535;
-    for (long long s0 = 0; s0 < nstates; s0 += max_y * S) {
+    for (long long s0 = 0; op->nitems > 0 && s0 < nstates; s0 += max_y * S) {
         const long long ns = std::min(nstates - s0, max_y * S);
         dim3 grid((unsigned)op->nitems, (unsigned)((ns + S - 1) / S));
         if (op->k_complex)

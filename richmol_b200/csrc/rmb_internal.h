@@ -18,8 +18,8 @@ struct ProdD {
     long long ent_off;   // offset of the MF table (row 0) in the global entry pool
     int dk2;             // ket dim_k
     int dm2;             // ket dim_m
-    int nd;              // ELL width of the MF table
-    int pad;
+    int nd;              // ELL width (number of diagonals) of the MF table
+    int tab;             // global MF table index (slot masks)
 };
 
 // one work item of the matvec: a tile of rows (m1) x columns (k1) of one bra block
@@ -32,9 +32,15 @@ struct ItemD {
     int dk2max;          // max ket dim_k over those products
 };
 
+// tiled matvec (rmb_matvec.cuh)
+struct Item2D;
+struct XRange;
+struct Unit2D;
+
 struct PartH {
     int ncart = 0;
     long long ent_begin = 0, ent_end = 0;   // range in the global entry pool
+    int tab_begin = 0, tab_end = 0;         // range of global MF table indices
     cplx* d_coef = nullptr;                 // [ncart][nent]
     double* d_fprod = nullptr;              // [ncart]
     bool has_field = false;
@@ -68,13 +74,30 @@ struct rmb_operator {
     rmb::ItemD* d_items = nullptr;
     int* d_ent_col = nullptr;
     rmb::cplx* d_ent_val = nullptr;
+    int* d_ent_tab = nullptr;        // entry -> global table index
+    int* d_tab_off = nullptr;        // [ntab] first entry of each table (int: nent < 2^31)
+    int* d_tab_nd = nullptr;         // [ntab] ELL width
+    unsigned* d_tab_mask = nullptr;  // [ntab] bit j set <=> diagonal slot j has a non-zero MF entry
+    int ntab = 0;
     double* d_kpool = nullptr;       // doubles, or interleaved complex if k_complex
     int* d_flags = nullptr;          // [0] mf non-empty flag (per set_field accumulates), [1..] scratch
     std::vector<rmb::PartH> parts;
     std::vector<rmb::ItemD> h_items;
     std::vector<rmb::ProdD> h_prods;
-    size_t matvec_smem = 0;          // dynamic shared memory of the matvec launch
-    int matvec_S = 1;                // states per CTA
+    size_t matvec_smem = 0;          // dynamic shared memory of the scalar matvec launch
+    int matvec_S = 1;                // states per CTA (scalar kernel)
+    // tiled matvec
+    int nitems2 = 0;
+    void* d_items2 = nullptr;        // Item2D[]
+    void* d_xranges = nullptr;       // XRange[]
+    void* d_units = nullptr;         // Unit2D[] for `units_nstates` states
+    long long units_nstates = -1;
+    int nunits = 0;
+    int units_cap = 0;
+    std::vector<int> h_item2_states; // states per CTA of each tiled item
+    int kt_doubles = 0;
+    int xbuf_elems = 0;
+    size_t matvec2_smem = 0;
     // algorithmic work per state-matvec (for DESIGN.md / bench roofline)
     double flops_per_state = 0;
     double op_bytes = 0;

@@ -64,7 +64,10 @@ __device__ __forceinline__ double warp_reduce_partials(const double* p, int n, i
 // ------------------------------------------------------------------------------------------
 __global__ void k_field_contract(long long nent, int ncart, const cplx* __restrict__ coef,
                                  const double* __restrict__ fprod, double thresh, int all_dropped,
-                                 cplx* __restrict__ val, int* __restrict__ nz_flag) {
+                                 cplx* __restrict__ val, int* __restrict__ nz_flag,
+                                 const int* __restrict__ ent_tab, const int* __restrict__ tab_off,
+                                 const int* __restrict__ tab_nd, unsigned* __restrict__ tab_mask,
+                                 long long ent_begin) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= nent) return;
     cplx acc = make_double2(0.0, 0.0);
@@ -80,7 +83,13 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
         if (thresh > 0.0 && hypot(acc.x, acc.y) < thresh) acc = make_double2(0.0, 0.0);
     }
     val[e] = acc;
-    if (acc.x != 0.0 || acc.y != 0.0) *nz_flag = 1;
+    if (acc.x != 0.0 || acc.y != 0.0) {
+        *nz_flag = 1;
+        // diagonal slot of this entry inside its (diagonal-aligned) ELL table
+        const int t = ent_tab[ent_begin + e];
+        const int slot = (int)((ent_begin + e - tab_off[t]) % tab_nd[t]);
+        if (slot < 32) atomicOr(&tab_mask[t], 1u << slot);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

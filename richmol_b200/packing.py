@@ -198,25 +198,25 @@ class PackedPart:
 
 
 def _ell_table(dm1, dm2, coos, ncart):
-    """Union-pattern ELL table: returns (col[dm1*nd], coef[ncart, dm1*nd], nd)."""
+    """Diagonal-aligned ELL table over the union pattern: slot j of every row holds the entry on
+    diagonal (col - row) = diag[j] (or -1 where that diagonal leaves the matrix), so a diagonal that
+    vanishes after the field contraction vanishes for the whole table.
+    Returns (col[dm1*nd], coef[ncart, dm1*nd], nd)."""
     if coos:
-        keys = np.concatenate([m.row.astype(np.int64) * dm2 + m.col.astype(np.int64) for _, m in coos])
-        uniq = np.unique(keys)
+        rows = np.concatenate([m.row.astype(np.int64) for _, m in coos])
+        cols = np.concatenate([m.col.astype(np.int64) for _, m in coos])
     else:
-        uniq = np.zeros(0, dtype=np.int64)
-    rows_u = (uniq // dm2).astype(np.int64)
-    counts = np.bincount(rows_u, minlength=dm1) if len(uniq) else np.zeros(dm1, dtype=np.int64)
-    nd = max(1, int(counts.max()) if dm1 > 0 else 1)
-    start = np.zeros(dm1 + 1, dtype=np.int64)
-    np.cumsum(counts, out=start[1:])
-    j = np.arange(len(uniq), dtype=np.int64) - start[rows_u]
-    ent = rows_u * nd + j
+        rows = cols = np.zeros(0, dtype=np.int64)
+    diags = np.unique(cols - rows)
+    nd = max(1, len(diags))
     col = np.full(dm1 * nd, -1, dtype=np.int32)
-    col[ent] = (uniq % dm2).astype(np.int32)
     coef = np.zeros((ncart, dm1 * nd), dtype=np.complex128)
-    for ci, m in coos:
-        pos = np.searchsorted(uniq, m.row.astype(np.int64) * dm2 + m.col.astype(np.int64))
-        np.add.at(coef[ci], ent[pos], m.data)
+    if len(diags):
+        ent_all = rows * nd + np.searchsorted(diags, cols - rows)
+        col[ent_all] = cols.astype(np.int32)
+        for ci, m in coos:
+            r, c = m.row.astype(np.int64), m.col.astype(np.int64)
+            np.add.at(coef[ci], r * nd + np.searchsorted(diags, c - r), m.data)
     return col, coef, nd
 
 
