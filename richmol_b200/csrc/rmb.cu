@@ -61,6 +61,8 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_units);
     cudaFree(op->d_ent_col);
     cudaFree(op->d_ent_val);
+    cudaFree(op->d_ent_cval);
+    cudaFree(op->d_ent_ccol);
     cudaFree(op->d_ent_tab);
     cudaFree(op->d_tab_off);
     cudaFree(op->d_tab_nd);
@@ -73,12 +75,14 @@ void rmb_operator_destroy(rmb_operator* op) {
     }
     for (auto* s : op->slabs) cudaFree(s);
     cudaFree(op->d_w);
-    cudaFree(op->d_W);
     cudaFree(op->d_slab_ptrs);
     cudaFree(op->d_alpha);
     cudaFree(op->d_beta);
     cudaFree(op->d_ccur);
     cudaFree(op->d_dc);
+    cudaFree(op->d_rinv);
+    cudaFree(op->d_ceff);
+    for (auto e : op->it_events) cudaEventDestroy(e);
     cudaFree(op->d_active);
     cudaFree(op->d_order);
     cudaFree(op->d_pdot);
@@ -225,7 +229,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
     std::vector<XRange> xranges;
-    const size_t smem_budget = 110 * 1024;   // two CTAs per SM
+    const size_t smem_budget = 108 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
     for (int b = 0; b < d->nblocks; ++b) {
         const int dk1 = d->blk_dk[b], dm1 = d->blk_dm[b];
         if (dk1 == 0 || dm1 == 0) continue;
@@ -242,28 +246,28 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         //      chunks (<= 16); falls back to the scalar kernel when the tile does not fit
         bool fast = !force_scalar && ndmax <= MV2_NDMAX;   // diagonal slots handled in registers
         if (fast) {
-            int best_nt = 0, best_pairs = 0;
+            int best_nt = 0, best_nst = 0;
             double best_util = -1;
             const int nt0 = (dm1 + MV2_THREADS - 1) / MV2_THREADS;
             for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
                 const int nr = (dm1 + nt - 1) / nt;
-                int pairs = std::min(16, MV2_THREADS / nr);
-                // shared memory: K^T of all products + two ket-row buffers
-                auto need = [&](int pr_) {
+                int nst = std::min(MV2_SMAX, MV2_THREADS / nr);
+                // shared memory: K^T of all products + two ket-row buffers + descriptors
+                auto need = [&](int nst_) {
                     size_t kt = 0, xb = 0;
                     for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
                         const ProdD& q = op->h_prods[p];
                         const int nc0 = std::min(dk1, MV2_NCMAX);
                         const int ncp = nc0 == 1 ? 1 : ((nc0 + 1) & ~1);
-                        kt += (size_t)q.dk2 * ncp * (kc ? 2 : 1) * 8;
-                        xb = std::max(xb, (size_t)2 * pr_ * std::min(q.dm2, nr + 2 * q.nd) * (q.dk2 | 1) * 16);
+                        kt += (size_t)q.dk2 * ncp * (kc ? 2 : 1) * 8 + sizeof(ProdS);
+                        xb = std::max(xb, (size_t)nst_ * std::min(q.dm2, nr + 2 * q.nd) * (q.dk2 | 1) * 16);
                     }
-                    return kt + 2 * xb;
+                    return kt + 2 * xb + (size_t)2 * MV2_NDMAX * nr * 20 + MV2_SMAX * 8 + 64;
                 };
-                while (pairs > 1 && need(pairs) > smem_budget) --pairs;
-                if (need(pairs) > smem_budget) continue;
-                const double util = (double)nr * pairs / MV2_THREADS * ((double)dm1 / (nr * nt));
-                if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_pairs = pairs; }
+                while (nst > 1 && need(nst) > smem_budget) --nst;
+                if (need(nst) > smem_budget) continue;
+                const double util = (double)nr * nst / MV2_THREADS * ((double)dm1 / (nr * nt));
+                if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_nst = nst; }
             }
             if (best_nt == 0) fast = false;
             if (fast) {
@@ -273,13 +277,14 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         Item2D it;
                         it.bra_off = d->blk_off[b];
                         it.dk1 = dk1;
+                        it.dm1 = dm1;
                         it.r0 = r0;
                         it.nrows = std::min(nr_t, dm1 - r0);
                         it.c0 = c0;
                         it.nc = std::min(MV2_NCMAX, dk1 - c0);
                         it.p_begin = bra_begin[b];
                         it.p_end = bra_begin[b + 1];
-                        it.pairs = best_pairs;
+                        it.nst = best_nst;
                         it.xr_off = (int)xranges.size();
                         const int ncp = it.nc == 1 ? 1 : ((it.nc + 1) & ~1);
                         int ktd = 0;
@@ -296,10 +301,12 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             xr.c_lo = hi < 0 ? 0 : lo;
                             xr.nr = hi < 0 ? 0 : hi - lo + 1;
                             xranges.push_back(xr);
-                            op->xbuf_elems = std::max(op->xbuf_elems, 2 * it.pairs * xr.nr * (q.dk2 | 1));
+                            op->xbuf_elems = std::max({op->xbuf_elems, it.nst * xr.nr * (q.dk2 | 1), 256});
                         }
                         it.kt_total = ktd;
                         op->kt_doubles = std::max(op->kt_doubles, (ktd + 1) & ~1);
+                        op->np_max = std::max(op->np_max, it.p_end - it.p_begin);
+                        op->mf_elems = std::max(op->mf_elems, MV2_NDMAX * it.nrows);
                         items2.push_back(it);
                     }
                 continue;
@@ -345,8 +352,9 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         items2.swap(sorted);
     }
     op->nitems2 = (int)items2.size();
-    for (auto& it : items2) op->h_item2_states.push_back(2 * it.pairs);
-    op->matvec2_smem = (size_t)op->kt_doubles * 8 + (size_t)2 * op->xbuf_elems * 16;
+    for (auto& it : items2) op->h_item2_states.push_back(it.nst);
+    op->matvec2_smem = (size_t)op->kt_doubles * 8 + (size_t)2 * op->xbuf_elems * 16 + (size_t)op->np_max * sizeof(ProdS) +
+                       (size_t)2 * op->mf_elems * 20 + MV2_SMAX * 8;
     opbytes += 20.0 * (double)op->nent;   // MF values + column indices
     op->flops_per_state = flops;
     op->op_bytes = opbytes;
@@ -378,12 +386,17 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     }
     if ((rc = upload(&op->d_ent_col, ent_col.data(), ent_col.size()))) return rc;
     if ((rc = upload<cplx>(&op->d_ent_val, nullptr, (size_t)op->nent))) return rc;
+    if ((rc = upload<cplx>(&op->d_ent_cval, nullptr, (size_t)op->nent))) return rc;
+    if ((rc = upload<int>(&op->d_ent_ccol, nullptr, (size_t)op->nent))) return rc;
+    RMB_CUDA(cudaMemset(op->d_ent_cval, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
+    RMB_CUDA(cudaMemset(op->d_ent_ccol, 0xff, std::max<size_t>(1, (size_t)op->nent) * sizeof(int)));
     op->ntab = (int)tab_off.size();
+    tab_off.push_back((int)ent_col.size());   // extent of the last table
     if ((rc = upload(&op->d_ent_tab, ent_tab.data(), ent_tab.size()))) return rc;
     if ((rc = upload(&op->d_tab_off, tab_off.data(), tab_off.size()))) return rc;
     if ((rc = upload(&op->d_tab_nd, tab_nd.data(), tab_nd.size()))) return rc;
-    if ((rc = upload<unsigned>(&op->d_tab_mask, nullptr, tab_off.size()))) return rc;
-    RMB_CUDA(cudaMemset(op->d_tab_mask, 0, std::max<size_t>(1, tab_off.size()) * sizeof(unsigned)));
+    if ((rc = upload<unsigned>(&op->d_tab_mask, nullptr, (size_t)op->ntab + 1))) return rc;
+    RMB_CUDA(cudaMemset(op->d_tab_mask, 0, ((size_t)op->ntab + 1) * sizeof(unsigned)));
     RMB_CUDA(cudaMemset(op->d_ent_val, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
     if ((rc = upload(&op->d_kpool, kpool.data(), kpool.size()))) return rc;
     if ((rc = upload<int>(&op->d_flags, nullptr, (size_t)d->nparts + 1))) return rc;
@@ -426,8 +439,11 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
         k_field_contract<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ncart, ph.d_coef, ph.d_fprod, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
             op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, ph.ent_begin);
+        k_compact_tables<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
+            nent, ph.ent_begin, op->d_ent_val, op->d_ent_col, op->d_ent_tab, op->d_tab_off, op->d_tab_nd,
+            op->d_tab_mask, op->d_ent_cval, op->d_ent_ccol);
         RMB_CUDA(cudaGetLastError());
-        op->n_launches++;
+        op->n_launches += 2;
     }
     ph.has_field = true;
     ph.all_dropped = all_dropped != 0;
@@ -475,8 +491,15 @@ static int check_field(rmb_operator* op) {
     return RMB_OK;
 }
 
+struct MvEpilogue {
+    const double* scale = nullptr;   // per-state factor applied to the product (rinv_k), stride in doubles
+    int scale_stride = 0;
+    cplx* pdot = nullptr;            // fused partial sums conj(y) * x per (state, tiled item)
+    int npart = 0;
+};
+
 static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
-                         long long ldy, const int* active, cudaStream_t st) {
+                         long long ldy, const int* active, cudaStream_t st, const MvEpilogue& ep = MvEpilogue()) {
     if ((op->nitems == 0 && op->nitems2 == 0) || nstates == 0) return RMB_OK;
     const int S = op->matvec_S;
     const int zstride = (int)(op->matvec_smem / (S * sizeof(cplx)));
@@ -512,18 +535,21 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         if (op->k_complex)
             k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
                 (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                op->d_ent_col, op->d_ent_val, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
-                op->kt_doubles, op->xbuf_elems);
+                op->d_ent_ccol, op->d_ent_cval, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                op->np_max, op->kt_doubles, op->xbuf_elems, op->mf_elems, ep.scale, ep.scale_stride, ep.pdot,
+                ep.npart);
         else
             k_matvec_tiled<false><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
                 (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                op->d_ent_col, op->d_ent_val, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
-                op->kt_doubles, op->xbuf_elems);
+                op->d_ent_ccol, op->d_ent_cval, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                op->np_max, op->kt_doubles, op->xbuf_elems, op->mf_elems, ep.scale, ep.scale_stride, ep.pdot,
+                ep.npart);
         op->n_launches++;
     }
-    // grid.y is limited to 65535: loop over slices of states
+    // scalar kernel for the bra blocks the tiled kernel does not cover (no fused epilogue: callers
+    // check op->nitems == 0 before asking for one); grid.y is limited to 65535
     const long long max_y = 65535;
-    for (long long s0 = 0; op->nitems > 0 && s0 < nstates; s0 += max_y * S) {
+    for (long long s0 = 0; op->nitems > 0 && Y != nullptr && s0 < nstates; s0 += max_y * S) {
         const long long ns = std::min(nstates - s0, max_y * S);
         dim3 grid((unsigned)op->nitems, (unsigned)((ns + S - 1) / S));
         if (op->k_complex)
@@ -553,7 +579,11 @@ static int ensure(T** p, size_t count) {
     return RMB_OK;
 }
 
-// (re)allocate the per-state small arrays and the w / W vectors for `cap` states
+// the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
+static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 > 0; }
+static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 : op->nchunk; }
+
+// (re)allocate the per-state small arrays and the product vector for `cap` states
 static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     if (cap <= op->ws_states && maxorder <= op->ws_maxorder && op->d_w) return RMB_OK;
     cap = std::max(cap, op->ws_states);
@@ -565,20 +595,26 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     op->nchunk = nchunks(op->n);
     int rc;
     const size_t vec = (size_t)cap * (size_t)op->n;
+    const size_t np = (size_t)std::max(op->nchunk, op->nitems2);
     if ((rc = ensure(&op->d_w, vec))) return rc;
-    if ((rc = ensure(&op->d_W, vec))) return rc;
     if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
     if ((rc = ensure(&op->d_beta, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->d_rinv, (size_t)cap * (maxorder + 1)))) return rc;
     if ((rc = ensure(&op->d_ccur, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->d_ceff, (size_t)cap * maxorder))) return rc;
     if ((rc = ensure(&op->d_dc, (size_t)cap * maxorder))) return rc;
     if ((rc = ensure(&op->d_active, (size_t)cap))) return rc;
     if ((rc = ensure(&op->d_order, (size_t)cap))) return rc;
-    if ((rc = ensure(&op->d_pdot, (size_t)cap * op->nchunk))) return rc;
+    if ((rc = ensure(&op->d_pdot, (size_t)cap * np))) return rc;
     if ((rc = ensure(&op->d_pnrm, (size_t)cap * op->nchunk))) return rc;
     if ((rc = ensure(&op->d_pconv, (size_t)cap * op->nchunk))) return rc;
-    if (!op->d_ctrl) {
-        if ((rc = ensure(&op->d_ctrl, 4))) return rc;
-        RMB_CUDA(cudaMallocHost((void**)&op->h_ctrl, 4 * sizeof(int)));
+    if ((rc = ensure(&op->d_ctrl, (size_t)4 * (maxorder + 2)))) return rc;
+    if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
+    RMB_CUDA(cudaMallocHost((void**)&op->h_ctrl, sizeof(int) * 4 * (maxorder + 2)));
+    while ((int)op->it_events.size() < maxorder + 2) {
+        cudaEvent_t e;
+        RMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        op->it_events.push_back(e);
     }
     op->ws_states = cap;
     op->ws_maxorder = maxorder;
@@ -599,14 +635,22 @@ static int ensure_slab(rmb_operator* op, int k, cudaStream_t st) {
         RMB_CUDA(cudaMalloc((void**)&op->d_slab_ptrs, op->slab_ptrs_cap * sizeof(cplx*)));
     }
     if (op->slab_ptrs_uploaded != (int)op->slabs.size()) {
+        RMB_CUDA(cudaStreamSynchronize(st));   // kernels in flight read the table; slabs.data() is pageable
         RMB_CUDA(cudaMemcpyAsync(op->d_slab_ptrs, op->slabs.data(), op->slabs.size() * sizeof(cplx*),
                                  cudaMemcpyHostToDevice, st));
+        RMB_CUDA(cudaStreamSynchronize(st));
         op->slab_ptrs_uploaded = (int)op->slabs.size();
     }
     return RMB_OK;
 }
 
 // One sub-batch of states through the literal Lanczos loop of tdse.py:417-486.
+//
+// Launches per iteration: matvec (+ fused scale and <w,V_k> partials), k_small_a (alpha, small
+// exponential), k_recur_conv (three-term recurrence + convergence metric), k_small_b (beta, stop rule,
+// zero-beta fallback).  The host does not block on every iteration: the control word of iteration k
+// is copied back asynchronously and inspected after iteration k+1 has been enqueued, so the GPU
+// never idles on the host; the price is one enqueued iteration in which every state is inactive.
 static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol,
                          int maxorder, const cplx* ph, int* orders_host, cudaStream_t st,
                          bool* hit_maxorder) {
@@ -614,61 +658,66 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     const int nch = op->nchunk;
     const dim3 vgrid((unsigned)nch, (unsigned)B);
     const int ts = op->ws_maxorder, bs = op->ws_maxorder + 1;
+    const bool fused = fused_dot(op);
+    const int npart = dot_parts(op);
     int rc;
-    if ((rc = ensure_slab(op, 1, st))) return rc;
-    k_fill_int<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, 1, (int)B);
-    k_fill_int<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_order, 0, (int)B);
+    if ((rc = ensure_slab(op, 2, st))) return rc;
+    RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
+    k_init_states<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, op->d_order, op->d_rinv,
+                                                               op->d_beta, bs, (int)B);
     k_phase_init<<<vgrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], n, n);
-    op->n_launches += 3;
-    long long n_active = B;
-    int k = 0;
+    op->n_launches += 2;
+    int k = 0, last = -1;
+    std::vector<long long> act_hist;
     for (;; ++k) {
         if ((rc = ensure_slab(op, k + 1, st))) return rc;
         cplx* Vk = op->slabs[k];
-        if (k > 0) {
-            // V_k = W_{k-1} / beta_k  (or the Gram-Schmidt fallback when beta_k == 0)
-            k_scale<<<vgrid, VEC_THREADS, 0, st>>>(op->d_W, Vk, n, n, op->d_beta, bs, k, op->d_active);
-            op->n_launches++;
-            if (op->h_ctrl[2] > 0) {
-                k_fallback_ones<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_beta, bs, k,
-                                                                     op->d_active);
-                op->n_launches++;
-            }
+        MvEpilogue ep;
+        if (fused) {
+            ep.scale = op->d_rinv + k;
+            ep.scale_stride = bs;
+            ep.pdot = op->d_pdot;
+            ep.npart = npart;
         }
-        if ((rc = launch_matvec(op, Vk, op->d_w, B, n, n, op->d_active, st))) return rc;
-        op->n_state_matvecs += n_active;
-        k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, n, n, op->d_pdot, nch, op->d_active);
-        k_recur<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, k > 0 ? op->slabs[k - 1] : nullptr, op->d_W, n, n,
-                                               op->d_pdot, nch, op->d_alpha, op->d_beta, ts, bs, k,
-                                               op->d_pnrm, op->d_active);
-        k_small<<<(unsigned)B, 32, 0, st>>>(op->d_pnrm, nch, op->d_alpha, op->d_beta, ts, bs, k, fac,
-                                            op->d_ccur, op->d_dc, op->d_active);
-        op->n_launches += 3;
-        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, 4 * sizeof(int), st));
-        if (k > 0) {
-            k_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_dc, ts, k, op->d_pconv, nch,
-                                                  op->d_active);
-            k_decide<<<(unsigned)B, 32, 0, st>>>(op->d_pconv, nch, tol, k, maxorder, op->d_active,
-                                                 op->d_order, op->d_ctrl);
+        if ((rc = launch_matvec(op, Vk, op->d_w, B, n, n, op->d_active, st, ep))) return rc;
+        if (!fused) {
+            // some bra blocks went through the scalar kernel, which has no epilogue: scale the product
+            // (w = rinv_k * H slab_k) and form the partial dots in separate passes
+            k_scale_rows<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, n, n, op->d_rinv + k, bs, op->d_active);
+            k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, n, n, op->d_pdot, npart, op->d_active);
             op->n_launches += 2;
         }
-        k_count_zero_beta<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_beta, bs, k + 1, op->d_active,
-                                                                        (int)B, op->d_ctrl);
-        op->n_launches++;
+        k_small_a<<<(unsigned)B, 32, 0, st>>>(op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, ts, bs, k,
+                                              fac, op->d_ccur, op->d_ceff, op->d_dc, op->d_active);
+        k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, n, n, op->d_alpha, op->d_beta,
+                                                    op->d_rinv, op->d_dc, ts, bs, k, op->d_pnrm, op->d_pconv,
+                                                    nch, op->d_active);
+        k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_pnrm, op->d_pconv, nch, op->d_beta, op->d_rinv, bs, k,
+                                                       tol, maxorder, op->d_active, op->d_order, op->d_ctrl,
+                                                       op->d_slab_ptrs, n, n);
+        op->n_launches += 3;
         op->n_iterations++;
-        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        RMB_CUDA(cudaStreamSynchronize(st));
-        if (k > 0) n_active = op->h_ctrl[0];
-        if (op->h_ctrl[1]) *hit_maxorder = true;
-        if (k > 0 && n_active == 0) break;
-        if (k == 0 && maxorder <= 1) {   // `while k < maxorder` never entered (tdse.py:450,480)
-            *hit_maxorder = true;
+        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl + 4 * k, op->d_ctrl + 4 * k, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaEventRecord(op->it_events[k], st));
+        // inspect the previous iteration (its kernels have most likely finished by now)
+        if (k >= 1) {
+            RMB_CUDA(cudaEventSynchronize(op->it_events[k - 1]));
+            act_hist.push_back(op->h_ctrl[4 * (k - 1)]);
+            if (op->h_ctrl[4 * (k - 1) + 1]) *hit_maxorder = true;
+            if (op->h_ctrl[4 * (k - 1)] == 0) { last = k - 1; break; }
+        }
+        if (k + 1 >= maxorder + 1) {   // safety net: cannot happen (k_small_b retires every state)
+            RMB_CUDA(cudaEventSynchronize(op->it_events[k]));
             break;
         }
     }
-    k_combine<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_ccur, ts, op->d_order, ph, psi, ld);
+    (void)last;
+    k_combine<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_ceff, ts, op->d_order, ph, psi, ld);
     op->n_launches++;
     RMB_CUDA(cudaGetLastError());
+    // state-matvecs actually performed: all states in iteration 0, the survivors of k-1 in iteration k
+    op->n_state_matvecs += B;
+    for (long long a : act_hist) op->n_state_matvecs += a;
     if (orders_host) {
         RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         RMB_CUDA(cudaStreamSynchronize(st));
@@ -700,17 +749,24 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         set_error("maxorder must be in [1, 128]");
         return RMB_ERR_INVALID;
     }
-    // sub-batch size from the workspace budget: w, W and ~14 Krylov vectors per state
-    long long budget = op->ws_budget;
-    if (budget <= 0) {
-        size_t fr = 0, tot = 0;
-        RMB_CUDA(cudaMemGetInfo(&fr, &tot));
-        long long held = (long long)(op->slabs.size() + 2) * op->ws_states * n * (long long)sizeof(cplx);
-        budget = (long long)(0.4 * (double)(fr + (size_t)held));
+    // sub-batch size from the workspace budget: the product vector and ~15 Krylov vectors per state
+    long long bc = op->ws_states;
+    if (bc < std::min<long long>(nstates, 65535) && !(op->ws_states > 0 && op->ws_budget_fixed)) {
+        long long budget = op->ws_budget;
+        if (budget <= 0) {
+            size_t fr = 0, tot = 0;
+            RMB_CUDA(cudaMemGetInfo(&fr, &tot));
+            long long held = (long long)(op->slabs.size() + 1) * op->ws_states * n * (long long)sizeof(cplx);
+            budget = (long long)(0.4 * (double)(fr + (size_t)held));
+        }
+        const long long per_state = 16LL * n * (long long)sizeof(cplx);
+        bc = std::max(1LL, std::min({(long long)nstates, budget / per_state, 65535LL}));
+        if (bc <= op->ws_states) bc = op->ws_states;
+        op->ws_budget_fixed = true;   // the size is settled for this handle unless the budget is changed
     }
-    long long per_state = 16LL * n * (long long)sizeof(cplx);
-    long long bc = std::max(1LL, std::min({nstates, budget / per_state, 65535LL}));
+    bc = std::max(1LL, std::min(bc, (long long)nstates));
     if ((rc = ensure_workspace(op, bc, maxorder))) return rc;
+    bc = std::min<long long>(op->ws_states, nstates);
     bool hit = false;
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, nstates - s0);
@@ -811,10 +867,21 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, (long long)nstates - s0);
         const cplx* psi = (const cplx*)psi_dev + s0 * ld;
-        if ((rc = launch_matvec(op, psi, op->d_w, b, ld, n, nullptr, st))) return rc;
-        k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(psi, ld, op->d_w, n, n, op->d_pdot, nch);
-        k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, nch, (cplx*)expval_dev + s0);
-        op->n_launches += 2;
+        if (fused_dot(op)) {
+            // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
+            // the product vector itself is never written
+            MvEpilogue ep;
+            ep.pdot = op->d_pdot;
+            ep.npart = op->nitems2;
+            if ((rc = launch_matvec(op, psi, nullptr, b, ld, n, nullptr, st, ep))) return rc;
+            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, op->nitems2, (cplx*)expval_dev + s0, -1.0);
+            op->n_launches += 1;
+        } else {
+            if ((rc = launch_matvec(op, psi, op->d_w, b, ld, n, nullptr, st))) return rc;
+            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(psi, ld, op->d_w, n, n, op->d_pdot, nch);
+            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, nch, (cplx*)expval_dev + s0, 1.0);
+            op->n_launches += 2;
+        }
         op->n_state_matvecs += b;
     }
     RMB_CUDA(cudaGetLastError());
@@ -836,6 +903,7 @@ int32_t rmb_populations(const double* psi_dev, int64_t nstates, int64_t n, int64
 int32_t rmb_set_workspace_budget(rmb_operator* op, int64_t bytes) {
     if (!op) return RMB_ERR_INVALID;
     op->ws_budget = bytes;
+    op->ws_budget_fixed = false;
     return RMB_OK;
 }
 

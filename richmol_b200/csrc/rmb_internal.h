@@ -74,6 +74,8 @@ struct rmb_operator {
     rmb::ItemD* d_items = nullptr;
     int* d_ent_col = nullptr;
     rmb::cplx* d_ent_val = nullptr;
+    rmb::cplx* d_ent_cval = nullptr; // compacted (non-zero diagonals first) MF values per row
+    int* d_ent_ccol = nullptr;       // ... and their ket m index
     int* d_ent_tab = nullptr;        // entry -> global table index
     int* d_tab_off = nullptr;        // [ntab] first entry of each table (int: nent < 2^31)
     int* d_tab_nd = nullptr;         // [ntab] ELL width
@@ -97,6 +99,8 @@ struct rmb_operator {
     std::vector<int> h_item2_states; // states per CTA of each tiled item
     int kt_doubles = 0;
     int xbuf_elems = 0;
+    int np_max = 0;
+    int mf_elems = 0;                // MV2_NDMAX * max tile rows
     size_t matvec2_smem = 0;
     // algorithmic work per state-matvec (for DESIGN.md / bench roofline)
     double flops_per_state = 0;
@@ -107,7 +111,6 @@ struct rmb_operator {
     long long ws_states = 0;         // capacity in states of each slab
     std::vector<rmb::cplx*> slabs;   // V_0, V_1, ... each ws_states * n
     rmb::cplx* d_w = nullptr;        // H V_k
-    rmb::cplx* d_W = nullptr;        // residual W_k
     rmb::cplx** d_slab_ptrs = nullptr;   // device copy of slab pointers
     int slab_ptrs_cap = 0;
     int slab_ptrs_uploaded = 0;
@@ -116,13 +119,17 @@ struct rmb_operator {
     rmb::cplx* d_alpha = nullptr;    // [S][maxorder]
     double* d_beta = nullptr;        // [S][maxorder+1]
     rmb::cplx* d_ccur = nullptr;     // [S][maxorder]
-    rmb::cplx* d_dc = nullptr;       // [S][maxorder]
+    rmb::cplx* d_dc = nullptr;       // [S][maxorder] (c^k - c^{k-1}) * rinv
+    rmb::cplx* d_ceff = nullptr;     // [S][maxorder] c^k * rinv
+    double* d_rinv = nullptr;        // [S][maxorder+1] 1/beta_k (1 for k = 0 and after a fallback)
+    bool ws_budget_fixed = false;
+    std::vector<cudaEvent_t> it_events;
     int* d_active = nullptr;         // [S]
     int* d_order = nullptr;          // [S]
     rmb::cplx* d_pdot = nullptr;     // [S][nchunk]
     double* d_pnrm = nullptr;        // [S][nchunk]
     double* d_pconv = nullptr;       // [S][nchunk]
-    int* d_ctrl = nullptr;           // [0] n_active, [1] maxorder flag, [2] n_zero_beta
+    int* d_ctrl = nullptr;           // per iteration k: [4k] states still active, [4k+1] maxorder flag
     int* h_ctrl = nullptr;           // pinned mirror
     int nchunk = 0;
     // host staging for the *_host entry point

@@ -92,6 +92,33 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
     }
 }
 
+// K1b: compaction of the non-zero diagonals.  After k_field_contract the mask of table t tells which
+// diagonal slots carry any non-zero MF entry; the surviving diagonals are packed diagonal-major
+// (cval/ccol[tab_off + q*dm1 + row], q < popc(mask)), so the matvec only touches diagonals the field
+// actually couples and can stage them with contiguous copies.
+__global__ void k_compact_tables(long long nent, long long ent_begin, const cplx* __restrict__ val,
+                                 const int* __restrict__ col, const int* __restrict__ ent_tab,
+                                 const int* __restrict__ tab_off, const int* __restrict__ tab_nd,
+                                 const unsigned* __restrict__ tab_mask, cplx* __restrict__ cval,
+                                 int* __restrict__ ccol) {
+    const long long e = ent_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ent_begin + nent) return;
+    const int t = ent_tab[e];
+    const int nd = tab_nd[t];
+    const int rel = (int)(e - tab_off[t]);
+    const int r = rel / nd, j = rel - r * nd;
+    const unsigned mask = tab_mask[t];
+    if (j < 32 && ((mask >> j) & 1u)) {
+        const int q = __popc(mask & ((1u << j) - 1u));
+        const int c = col[e];
+        // rows of the table from its extent (tab_off has ntab + 1 entries)
+        const int dm1 = (tab_off[t + 1] - tab_off[t]) / nd;
+        const long long dst = (long long)tab_off[t] + (long long)q * dm1 + r;
+        cval[dst] = c >= 0 ? val[e] : make_double2(0.0, 0.0);
+        ccol[dst] = c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2 (scalar version): y = sum_p (MF_p (x) K_p) x   for one work item and a tile of states.
 // Z = MF_p * X_ket is staged in shared memory, then contracted with K_p.
@@ -178,6 +205,11 @@ k_matvec_scalar(const ItemD* __restrict__ items, const ProdD* __restrict__ prods
 
 // ------------------------------------------------------------------------------------------
 // Lanczos vector kernels.  Grid (nchunk, nstates); state-major vectors with leading dim ldv.
+//
+// Storage convention: slab 0 holds V_0 = psi*ph; slab k (k >= 1) holds the *unnormalised* residual
+// W_{k-1}, and the Krylov vector of the reference is V_k = slab_k * rinv_k with rinv_k = 1/beta_k
+// (tdse.py:455-456).  Every consumer applies rinv_k on the fly, which removes the separate
+// normalisation pass over the vector.
 // ------------------------------------------------------------------------------------------
 
 // V0 = psi * ph  (tdse.py:375), or a plain copy when ph == nullptr
@@ -213,66 +245,28 @@ k_phase_mul2(cplx* __restrict__ psi, long long ld, const cplx* __restrict__ ph, 
     }
 }
 
-// V_k = W_{k-1} / beta_k   (tdse.py:455-456); states with beta == 0 are left to k_fallback_ones
+// w *= rinv_k per state (only when the matvec could not apply the scale in its epilogue)
 __global__ void __launch_bounds__(VEC_THREADS)
-k_scale(const cplx* __restrict__ W, cplx* __restrict__ Vk, long long ldv, long long n,
-        const double* __restrict__ beta, int bstride, int k, const int* __restrict__ active) {
+k_scale_rows(cplx* __restrict__ w, long long ldv, long long n, const double* __restrict__ scale, int stride,
+             const int* __restrict__ active) {
     const long long s = blockIdx.y;
     if (!active[s]) return;
-    const double b = beta[s * bstride + k];
-    if (b == 0.0) return;
+    const double sc = scale[s * stride];
     const long long base = (long long)blockIdx.x * VEC_CHUNK;
 #pragma unroll
     for (int i = 0; i < VEC_PER_THREAD; ++i) {
         const long long x = base + threadIdx.x + i * VEC_THREADS;
         if (x < n) {
-            const cplx w = W[s * ldv + x];
-            Vk[s * ldv + x] = make_double2(w.x / b, w.y / b);
+            cplx v = w[s * ldv + x];
+            w[s * ldv + x] = make_double2(v.x * sc, v.y * sc);
         }
     }
 }
 
-// zero-beta fallback (tdse.py:459-465): V_k = normalised Gram-Schmidt of the all-ones vector
-// against V_0..V_{k-1}.  One CTA per state; only runs for states with beta_k == 0.
-__global__ void __launch_bounds__(VEC_THREADS)
-k_fallback_ones(cplx* const* __restrict__ slabs, long long ldv, long long n,
-                const double* __restrict__ beta, int bstride, int k, const int* __restrict__ active) {
-    __shared__ double sm[VEC_THREADS / 32];
-    __shared__ double2 bc;
-    const long long s = blockIdx.x;
-    if (!active[s] || beta[s * bstride + k] != 0.0) return;
-    cplx* v = slabs[k] + s * ldv;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(1.0, 0.0);
-    __syncthreads();
-    for (int j = 0; j < k; ++j) {
-        const cplx* vj = slabs[j] + s * ldv;
-        double pr = 0, pi = 0;   // proj = vdot(V_j, v) = sum conj(V_j) * v
-        for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
-            const cplx a = vj[x], b = v[x];
-            pr += a.x * b.x + a.y * b.y;
-            pi += a.x * b.y - a.y * b.x;
-        }
-        pr = block_sum<VEC_THREADS>(pr, sm);
-        pi = block_sum<VEC_THREADS>(pi, sm);
-        if (threadIdx.x == 0) bc = make_double2(pr, pi);
-        __syncthreads();
-        const cplx proj = bc;
-        for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = csub(v[x], cmul(proj, vj[x]));
-        __syncthreads();
-    }
-    double nr = 0;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) nr += cabs2(v[x]);
-    nr = block_sum<VEC_THREADS>(nr, sm);
-    if (threadIdx.x == 0) bc = make_double2(sqrt(nr), 0.0);
-    __syncthreads();
-    const double nv = bc.x;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(v[x].x / nv, v[x].y / nv);
-}
-
-// partial alpha: pdot[s][chunk] = sum conj(w) * V_k   (np.vdot(w, V[k]), tdse.py:445,468)
+// partial sum conj(w) * slab_k per chunk (used when the matvec did not fuse the dot product)
 __global__ void __launch_bounds__(VEC_THREADS)
 k_dot(const cplx* __restrict__ w, const cplx* __restrict__ Vk, long long ldv, long long n,
-      cplx* __restrict__ pdot, int nchunk, const int* __restrict__ active) {
+      cplx* __restrict__ pdot, int npart, const int* __restrict__ active) {
     __shared__ double sm[VEC_THREADS / 32];
     const long long s = blockIdx.y;
     if (active && !active[s]) return;
@@ -289,49 +283,7 @@ k_dot(const cplx* __restrict__ w, const cplx* __restrict__ Vk, long long ldv, lo
     }
     re = block_sum<VEC_THREADS>(re, sm);
     im = block_sum<VEC_THREADS>(im, sm);
-    if (threadIdx.x == 0) pdot[s * nchunk + blockIdx.x] = make_double2(re, im);
-}
-
-// W_k = w - alpha_k V_k - beta_k V_{k-1}   (tdse.py:446,469-470) + partial |W_k|^2
-__global__ void __launch_bounds__(VEC_THREADS)
-k_recur(const cplx* __restrict__ w, const cplx* __restrict__ Vk, const cplx* __restrict__ Vkm1,
-        cplx* __restrict__ W, long long ldv, long long n, const cplx* __restrict__ pdot, int nchunk,
-        cplx* __restrict__ alpha, const double* __restrict__ beta, int tstride, int bstride, int k,
-        double* __restrict__ pnrm, const int* __restrict__ active) {
-    __shared__ double sm[VEC_THREADS / 32];
-    __shared__ double2 s_alpha;
-    const long long s = blockIdx.y;
-    if (!active[s]) return;
-    if (threadIdx.x < 32) {
-        const double* p = reinterpret_cast<const double*>(pdot + s * nchunk);
-        const double re = warp_reduce_partials(p, nchunk, 2);
-        const double im = warp_reduce_partials(p + 1, nchunk, 2);
-        if (threadIdx.x == 0) {
-            s_alpha = make_double2(re, im);
-            if (blockIdx.x == 0) alpha[s * tstride + k] = make_double2(re, im);
-        }
-    }
-    __syncthreads();
-    const cplx a = s_alpha;
-    const double b = (k > 0) ? beta[s * bstride + k] : 0.0;
-    const long long base = (long long)blockIdx.x * VEC_CHUNK;
-    double nr = 0;
-#pragma unroll
-    for (int i = 0; i < VEC_PER_THREAD; ++i) {
-        const long long x = base + threadIdx.x + i * VEC_THREADS;
-        if (x < n) {
-            cplx r = csub(w[s * ldv + x], cmul(a, Vk[s * ldv + x]));
-            if (k > 0) {
-                const cplx vm = Vkm1[s * ldv + x];
-                r.x -= b * vm.x;
-                r.y -= b * vm.y;
-            }
-            W[s * ldv + x] = r;
-            nr += cabs2(r);
-        }
-    }
-    nr = block_sum<VEC_THREADS>(nr, sm);
-    if (threadIdx.x == 0) pnrm[s * nchunk + blockIdx.x] = nr;
+    if (threadIdx.x == 0) pdot[s * npart + blockIdx.x] = make_double2(re, im);
 }
 
 // First column of exp(fac * T), T symmetric tridiagonal (k+1 x k+1) with diagonal alpha[0..k] and
@@ -380,45 +332,86 @@ __device__ void warp_expm_col0(int n, const cplx* __restrict__ alpha, const doub
     }
 }
 
-// per state (one warp): beta_{k+1} = sqrt(sum |W_k|^2) (tdse.py:453), coefficients
-// c^k = expm(fac T_k)[:,0] and dc = c^k - c^{k-1} (tdse.py:474-475)
+// per state (one warp), after the matvec of iteration k:
+//   alpha_k = <w, V_k> (tdse.py:445,468) from the partial sums conj(w)*slab_k (times rinv_k),
+//   c^k = expm(fac T_k)[:,0] and dc = c^k - c^{k-1} (tdse.py:474-475); the coefficients are stored
+//   pre-multiplied by rinv_i so that u = sum_i ceff_i * slab_i.
 __global__ void __launch_bounds__(32)
-k_small(const double* __restrict__ pnrm, int nchunk, const cplx* __restrict__ alpha,
-        double* __restrict__ beta, int tstride, int bstride, int k, cplx fac,
-        cplx* __restrict__ ccur, cplx* __restrict__ dc, const int* __restrict__ active) {
+k_small_a(const cplx* __restrict__ pdot, int npart, cplx* __restrict__ alpha, const double* __restrict__ beta,
+          const double* __restrict__ rinv, int tstride, int bstride, int k, cplx fac,
+          cplx* __restrict__ ccur, cplx* __restrict__ ceff, cplx* __restrict__ dceff,
+          const int* __restrict__ active) {
     __shared__ double2 y[MAX_ORDER_SMEM], term[MAX_ORDER_SMEM], tmp[MAX_ORDER_SMEM];
     const long long s = blockIdx.x;
     if (!active[s]) return;
     const int lane = threadIdx.x;
-    const double nr = warp_reduce_partials(pnrm + s * nchunk, nchunk, 1);
-    if (lane == 0) beta[s * bstride + k + 1] = sqrt(nr);
+    const double* p = reinterpret_cast<const double*>(pdot + s * npart);
+    const double rk = rinv[s * bstride + k];
+    const double re = warp_reduce_partials(p, npart, 2) * rk;
+    const double im = warp_reduce_partials(p + 1, npart, 2) * rk;
+    if (lane == 0) alpha[s * tstride + k] = make_double2(re, im);
     if (k == 0) {
-        if (lane == 0) ccur[s * tstride] = make_double2(1.0, 0.0);   // u_0 = V_0
+        if (lane == 0) {
+            ccur[s * tstride] = make_double2(1.0, 0.0);   // u_0 = V_0
+            ceff[s * tstride] = make_double2(1.0, 0.0);
+        }
         return;
     }
+    __syncwarp();
     warp_expm_col0(k + 1, alpha + s * tstride, beta + s * bstride, fac, y, term, tmp);
     for (int i = lane; i <= k; i += 32) {
         const cplx prev = (i < k) ? ccur[s * tstride + i] : make_double2(0.0, 0.0);
-        dc[s * tstride + i] = csub(y[i], prev);
+        const double ri = rinv[s * bstride + i];
+        const cplx d = csub(y[i], prev);
+        dceff[s * tstride + i] = make_double2(d.x * ri, d.y * ri);
+        ceff[s * tstride + i] = make_double2(y[i].x * ri, y[i].y * ri);
         ccur[s * tstride + i] = y[i];
     }
 }
 
-// partial conv: pconv[s][chunk] = sum | sum_i dc_i V_i |^2  (u_k - u_{k-1}, tdse.py:475-476)
+// W_k = w - alpha_k V_k - beta_k V_{k-1}  (tdse.py:446,469-470) written to slab k+1, partial |W_k|^2,
+// and partial | sum_i dc_i V_i |^2  (u_k - u_{k-1}, tdse.py:475-476) in the same pass
 __global__ void __launch_bounds__(VEC_THREADS)
-k_conv(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* __restrict__ dc,
-       int tstride, int k, double* __restrict__ pconv, int nchunk, const int* __restrict__ active) {
+k_recur_conv(const cplx* __restrict__ w, cplx* const* __restrict__ slabs, long long ldv, long long n,
+             const cplx* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ rinv,
+             const cplx* __restrict__ dceff, int tstride, int bstride, int k, double* __restrict__ pnrm,
+             double* __restrict__ pconv, int nchunk, const int* __restrict__ active) {
     __shared__ double sm[VEC_THREADS / 32];
     __shared__ double2 sdc[MAX_ORDER_SMEM];
     const long long s = blockIdx.y;
     if (!active[s]) return;
-    for (int i = threadIdx.x; i <= k; i += VEC_THREADS) sdc[i] = dc[s * tstride + i];
+    for (int i = threadIdx.x; i <= k; i += VEC_THREADS) sdc[i] = dceff[s * tstride + i];
     __syncthreads();
+    const cplx a = alpha[s * tstride + k];
+    const double rk = rinv[s * bstride + k];
+    const double b = (k > 0) ? beta[s * bstride + k] : 0.0;
+    const double rkm1 = (k > 0) ? rinv[s * bstride + k - 1] : 0.0;
+    const cplx* sk = slabs[k] + s * ldv;
+    const cplx* skm1 = (k > 0) ? slabs[k - 1] + s * ldv : nullptr;
+    cplx* out = slabs[k + 1] + s * ldv;
     const long long base = (long long)blockIdx.x * VEC_CHUNK;
+    double nr = 0, cv = 0;
     cplx d[VEC_PER_THREAD];
 #pragma unroll
-    for (int i = 0; i < VEC_PER_THREAD; ++i) d[i] = make_double2(0.0, 0.0);
-    for (int j = 0; j <= k; ++j) {
+    for (int i = 0; i < VEC_PER_THREAD; ++i) {
+        const long long x = base + threadIdx.x + i * VEC_THREADS;
+        d[i] = make_double2(0.0, 0.0);
+        if (x < n) {
+            const cplx raw = sk[x];
+            const cplx vk = make_double2(raw.x * rk, raw.y * rk);
+            cplx r = csub(w[s * ldv + x], cmul(a, vk));
+            if (k > 0) {
+                const cplx rawm = skm1[x];
+                r.x -= b * (rawm.x * rkm1);
+                r.y -= b * (rawm.y * rkm1);
+                cfma(d[i], sdc[k], raw);
+                cfma(d[i], sdc[k - 1], rawm);
+            }
+            out[x] = r;
+            nr += cabs2(r);
+        }
+    }
+    for (int j = 0; j + 2 <= k; ++j) {
         const cplx* vj = slabs[j] + s * ldv;
         const cplx c = sdc[j];
 #pragma unroll
@@ -427,50 +420,101 @@ k_conv(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* 
             if (x < n) cfma(d[i], c, vj[x]);
         }
     }
-    double nr = 0;
 #pragma unroll
-    for (int i = 0; i < VEC_PER_THREAD; ++i) nr += cabs2(d[i]);
+    for (int i = 0; i < VEC_PER_THREAD; ++i) cv += cabs2(d[i]);
     nr = block_sum<VEC_THREADS>(nr, sm);
-    if (threadIdx.x == 0) pconv[s * nchunk + blockIdx.x] = nr;
-}
-
-// stop rule (tdse.py:450,478-484): a state leaves the loop when !(conv > tol); reaching
-// k == maxorder-1 raises even if that iteration converged.
-__global__ void __launch_bounds__(32)
-k_decide(const double* __restrict__ pconv, int nchunk, double tol, int k, int maxorder,
-         int* __restrict__ active, int* __restrict__ order, int* __restrict__ ctrl) {
-    const long long s = blockIdx.x;
-    if (!active[s]) return;
-    const double conv = warp_reduce_partials(pconv + s * nchunk, nchunk, 1);
+    cv = block_sum<VEC_THREADS>(cv, sm);
     if (threadIdx.x == 0) {
-        order[s] = k;
-        if (k == maxorder - 1) {
-            active[s] = 0;
-            atomicExch(&ctrl[1], 1);
-        } else if (!(conv > tol)) {
-            active[s] = 0;
-        } else {
-            atomicAdd(&ctrl[0], 1);
-        }
+        pnrm[s * nchunk + blockIdx.x] = nr;
+        pconv[s * nchunk + blockIdx.x] = cv;
     }
 }
 
-// count states whose next beta is exactly zero (they need the Gram-Schmidt fallback)
-__global__ void k_count_zero_beta(const double* __restrict__ beta, int bstride, int k,
-                                  const int* __restrict__ active, int nstates, int* __restrict__ ctrl) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < nstates && active[s] && beta[(long long)s * bstride + k] == 0.0) atomicAdd(&ctrl[2], 1);
+// per state (one CTA), end of iteration k:
+//   beta_{k+1} = sqrt(sum |W_k|^2) (tdse.py:453), rinv_{k+1};
+//   stop rule (tdse.py:450,478-484): a state leaves the loop when !(conv > tol); reaching
+//   k == maxorder-1 raises even if that iteration converged;
+//   zero-beta fallback (tdse.py:459-465): V_{k+1} = normalised Gram-Schmidt of the all-ones vector
+//   against V_0..V_k, written to slab k+1 with rinv = 1.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_small_b(const double* __restrict__ pnrm, const double* __restrict__ pconv, int nchunk,
+          double* __restrict__ beta, double* __restrict__ rinv, int bstride, int k, double tol, int maxorder,
+          int* __restrict__ active, int* __restrict__ order, int* __restrict__ ctrl,
+          cplx* const* __restrict__ slabs, long long ldv, long long n) {
+    __shared__ double sm[VEC_THREADS / 32];
+    __shared__ double2 bc;
+    __shared__ int s_fallback;
+    const long long s = blockIdx.x;
+    if (!active[s]) return;
+    if (threadIdx.x < 32) {
+        const double nr = warp_reduce_partials(pnrm + s * nchunk, nchunk, 1);
+        double conv = 1.0;
+        if (k > 0) conv = warp_reduce_partials(pconv + s * nchunk, nchunk, 1);
+        if (threadIdx.x == 0) {
+            const double b = sqrt(nr);
+            beta[s * bstride + k + 1] = b;
+            rinv[s * bstride + k + 1] = (b != 0.0) ? 1.0 / b : 1.0;
+            int still = 1;
+            if (k > 0) {
+                order[s] = k;
+                if (k == maxorder - 1) {
+                    still = 0;
+                    atomicExch(&ctrl[4 * k + 1], 1);
+                } else if (!(conv > tol)) {
+                    still = 0;
+                }
+            } else if (maxorder <= 1) {
+                still = 0;                               // `while k < maxorder` never entered
+                atomicExch(&ctrl[4 * k + 1], 1);
+            }
+            if (still) atomicAdd(&ctrl[4 * k], 1); else active[s] = 0;
+            s_fallback = (still && b == 0.0) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (!s_fallback) return;
+    // ---- Gram-Schmidt of ones against V_0..V_k (V_j = slab_j * rinv_j)
+    cplx* v = slabs[k + 1] + s * ldv;
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(1.0, 0.0);
+    __syncthreads();
+    for (int j = 0; j <= k; ++j) {
+        const cplx* vj = slabs[j] + s * ldv;
+        const double rj = rinv[s * bstride + j];
+        double pr = 0, pi = 0;   // proj = vdot(V_j, v) = sum conj(V_j) * v
+        for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
+            const cplx a = make_double2(vj[x].x * rj, vj[x].y * rj), b = v[x];
+            pr += a.x * b.x + a.y * b.y;
+            pi += a.x * b.y - a.y * b.x;
+        }
+        pr = block_sum<VEC_THREADS>(pr, sm);
+        pi = block_sum<VEC_THREADS>(pi, sm);
+        if (threadIdx.x == 0) bc = make_double2(pr, pi);
+        __syncthreads();
+        const cplx proj = bc;
+        for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
+            const cplx a = make_double2(vj[x].x * rj, vj[x].y * rj);
+            v[x] = csub(v[x], cmul(proj, a));
+        }
+        __syncthreads();
+    }
+    double nr = 0;
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) nr += cabs2(v[x]);
+    nr = block_sum<VEC_THREADS>(nr, sm);
+    if (threadIdx.x == 0) bc = make_double2(sqrt(nr), 0.0);
+    __syncthreads();
+    const double nv = bc.x;
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(v[x].x / nv, v[x].y / nv);
 }
 
-// psi = ph * sum_{i<=order} c_i V_i   (tdse.py:475,394)
+// psi = ph * sum_{i<=order} c_i V_i   (tdse.py:475,394), c_i V_i = ceff_i * slab_i
 __global__ void __launch_bounds__(VEC_THREADS)
-k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* __restrict__ ccur,
+k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* __restrict__ ceff,
           int tstride, const int* __restrict__ order, const cplx* __restrict__ ph,
           cplx* __restrict__ psi, long long ld) {
     __shared__ double2 sc[MAX_ORDER_SMEM];
     const long long s = blockIdx.y;
     const int k = order[s];
-    for (int i = threadIdx.x; i <= k; i += VEC_THREADS) sc[i] = ccur[s * tstride + i];
+    for (int i = threadIdx.x; i <= k; i += VEC_THREADS) sc[i] = ceff[s * tstride + i];
     __syncthreads();
     const long long base = (long long)blockIdx.x * VEC_CHUNK;
     cplx u[VEC_PER_THREAD];
@@ -489,6 +533,18 @@ k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cpl
     for (int i = 0; i < VEC_PER_THREAD; ++i) {
         const long long x = base + threadIdx.x + i * VEC_THREADS;
         if (x < n) psi[s * ld + x] = ph ? cmul(u[i], ph[x]) : u[i];
+    }
+}
+
+// per-state initialisation of a Lanczos batch
+__global__ void k_init_states(int* __restrict__ active, int* __restrict__ order, double* __restrict__ rinv,
+                              double* __restrict__ beta, int bstride, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        active[i] = 1;
+        order[i] = 0;
+        rinv[(long long)i * bstride] = 1.0;
+        beta[(long long)i * bstride] = 0.0;
     }
 }
 
@@ -521,12 +577,12 @@ k_dot2(const cplx* __restrict__ a, long long lda, const cplx* __restrict__ b, lo
 
 // final reduction of per-chunk partials to expval[s]
 __global__ void __launch_bounds__(32)
-k_reduce_dot(const cplx* __restrict__ pdot, int nchunk, cplx* __restrict__ out) {
+k_reduce_dot(const cplx* __restrict__ pdot, int nchunk, cplx* __restrict__ out, double imsign) {
     const long long s = blockIdx.x;
     const double* p = reinterpret_cast<const double*>(pdot + s * nchunk);
     const double re = warp_reduce_partials(p, nchunk, 2);
     const double im = warp_reduce_partials(p + 1, nchunk, 2);
-    if (threadIdx.x == 0) out[s] = make_double2(re, im);
+    if (threadIdx.x == 0) out[s] = make_double2(re, imsign * im);
 }
 
 // pop[i] = sum_s |psi_s[i]|^2

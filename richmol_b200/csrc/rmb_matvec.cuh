@@ -14,18 +14,18 @@
 
 namespace rmb {
 
-constexpr int MV2_THREADS = 128;
-constexpr int MV2_NCMAX = 16;     // columns (k1) per thread
+constexpr int MV2_THREADS = 256;
+constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
-constexpr int MV2_R = 2;          // states per thread
+constexpr int MV2_SMAX = 32;      // max states per CTA
 
 struct Item2D {
     long long bra_off;
-    int dk1;
+    int dk1, dm1;
     int r0, nrows;       // rows (m1) of the tile, nrows <= MV2_THREADS
     int c0, nc;          // columns (k1) of the tile, nc <= MV2_NCMAX
     int p_begin, p_end;
-    int pairs;           // state pairs per CTA (states per CTA = 2 * pairs)
+    int nst;             // states per CTA (threads = nst * nrows <= MV2_THREADS)
     int xr_off;          // offset into the per-(item, product) ket row ranges
     int kt_total;        // doubles of K^T staged in shared memory for this item
 };
@@ -33,190 +33,257 @@ struct Item2D {
 struct XRange { int c_lo, nr; };   // ket rows [c_lo, c_lo + nr) needed by (item, product)
 struct Unit2D { int item, s0; };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
+// per-product descriptor staged in shared memory at CTA start
+struct ProdS {
+    long long ket_off;   // + c_lo * dk2 already added
+    long long ent_off;   // first entry of the MF table
+    int dk2, nnz, c_lo, nr, xrs, pad0, pad1, pad2;
+};
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__device__ __forceinline__ int xrs_of(int dk2) { return dk2 | 1; }
-
-// stage the ket rows of product p for all states of the CTA (coalesced 16-byte cp.async copies)
-__device__ __forceinline__ void mv2_stage(double2* xb, const ProdD& pr, const XRange xr, const double2* X,
-                                          long long ldx, int s0, int nsl, const int* active, int nstates) {
-    const int xrs = xrs_of(pr.dk2);
-    const int per_state = xr.nr * pr.dk2;
+// Stage one product for all states of the CTA:
+//  * ket rows X[c_lo .. c_lo+nr) of every active state with coalesced 16-byte cp.async copies; rows are
+//    padded to an odd number of 16-byte words (bank-conflict-free row-strided reads),
+//  * the surviving MF diagonals of the tile rows (values + shared-memory offsets of their ket rows).
+__device__ __forceinline__ void mv2_stage(double2* xb, double2* mfs, int* xos, const ProdS& pr,
+                                          const Item2D& it, const double2* __restrict__ X,
+                                          const long long* __restrict__ sbase, const double2* __restrict__ cval,
+                                          const int* __restrict__ ccol) {
+    const int per_state = pr.nr * pr.dk2;
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(xb);
+    const unsigned sstride = (unsigned)(pr.nr * pr.xrs) * 16u;
+    const double2* src0 = X + pr.ket_off;
+    // element e = rl * dk2 + k2 advances by MV2_THREADS per iteration
     const float inv = 1.0f / (float)pr.dk2;
-    for (int s = 0; s < nsl; ++s) {
-        const int st = s0 + s;
-        if (st >= nstates || (active != nullptr && !active[st])) continue;
-        const double2* src = X + (long long)st * ldx + pr.ket_off + (long long)xr.c_lo * pr.dk2;
-        double2* dst = xb + (long long)s * xr.nr * xrs;
-        if (xrs == pr.dk2) {
-            for (int e = threadIdx.x; e < per_state; e += MV2_THREADS) cp_async16(dst + e, src + e);
-        } else {
-            for (int e = threadIdx.x; e < per_state; e += MV2_THREADS) {
-                const int rl = __float2int_rz(((float)e + 0.5f) * inv);   // exact for e < 2^21
-                cp_async16(dst + e + rl, src + e);                        // rl * xrs + k2 = e + rl
-            }
+    int rl = __float2int_rz(((float)threadIdx.x + 0.5f) * inv);
+    int k2 = threadIdx.x - rl * pr.dk2;
+    const int q256 = __float2int_rz(((float)MV2_THREADS + 0.5f) * inv);
+    const int r256 = MV2_THREADS - q256 * pr.dk2;
+    for (int e = threadIdx.x; e < per_state; e += MV2_THREADS) {
+        const unsigned off = (unsigned)(rl * pr.xrs + k2) * 16u;
+        const double2* src = src0 + e;
+#pragma unroll 4
+        for (int s = 0; s < it.nst; ++s) {
+            const long long sb = sbase[s];
+            if (sb >= 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + s * sstride + off), "l"(src + sb));
         }
+        k2 += r256;
+        rl += q256;
+        if (k2 >= pr.dk2) { k2 -= pr.dk2; ++rl; }
+    }
+    // MF diagonals: mfs[q][rl], xos[q][rl]
+    const int n = pr.nnz * it.nrows;
+    for (int idx = threadIdx.x; idx < n; idx += MV2_THREADS) {
+        const int q = idx / it.nrows, r = idx - q * it.nrows;
+        const long long e = pr.ent_off + (long long)q * it.dm1 + it.r0 + r;
+        const int col = ccol[e];
+        mfs[q * it.nrows + r] = cval[e];
+        xos[q * it.nrows + r] = col >= 0 ? (col - pr.c_lo) * pr.xrs : 0;   // value is 0 off the block edge
     }
 }
 
+// one block product for one thread: acc[k1] += sum_k2 K[k1,k2] * (sum_q MF[q] * X[row_q, k2])
 template <int NC, int NNZ, bool KC>
-__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const double2* __restrict__ xb,
-                                          const double2 (&mf)[MV2_NDMAX], const int (&xo)[MV2_NDMAX],
-                                          const double* __restrict__ ktp, int dk2, double2 (&accA)[NC],
-                                          double2 (&accB)[NC]) {
-    constexpr int NCP = NC;   // NC is even (or 1) for real K: rows of K^T are padded by the caller
+__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const double2* __restrict__ mfs,
+                                          const int* __restrict__ xos, int nrows,
+                                          const double* __restrict__ ktp, int dk2, double2 (&acc)[NC]) {
+    double2 mf[NNZ];
+    int xo[NNZ];
+#pragma unroll
+    for (int q = 0; q < NNZ; ++q) {
+        mf[q] = mfs[q * nrows];
+        xo[q] = xos[q * nrows];
+    }
 #pragma unroll 2
     for (int k2 = 0; k2 < dk2; ++k2) {
-        double2 zA = make_double2(0.0, 0.0), zB = make_double2(0.0, 0.0);
+        double2 z = make_double2(0.0, 0.0);
 #pragma unroll
         for (int q = 0; q < NNZ; ++q) {
-            const double2 a = xa[xo[q] + k2], b = xb[xo[q] + k2];
-            zA.x += mf[q].x * a.x - mf[q].y * a.y;
-            zA.y += mf[q].x * a.y + mf[q].y * a.x;
-            zB.x += mf[q].x * b.x - mf[q].y * b.y;
-            zB.y += mf[q].x * b.y + mf[q].y * b.x;
+            const double2 a = xa[xo[q] + k2];
+            z.x = fma(mf[q].x, a.x, z.x);
+            z.y = fma(mf[q].x, a.y, z.y);
+            z.x = fma(-mf[q].y, a.y, z.x);
+            z.y = fma(mf[q].y, a.x, z.y);
         }
         if (KC) {
-            const double2* krow = reinterpret_cast<const double2*>(ktp) + k2 * NCP;
+            const double2* krow = reinterpret_cast<const double2*>(ktp) + k2 * NC;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const double2 kv = krow[c];
-                accA[c].x += kv.x * zA.x - kv.y * zA.y;
-                accA[c].y += kv.x * zA.y + kv.y * zA.x;
-                accB[c].x += kv.x * zB.x - kv.y * zB.y;
-                accB[c].y += kv.x * zB.y + kv.y * zB.x;
+                acc[c].x = fma(kv.x, z.x, acc[c].x);
+                acc[c].y = fma(kv.x, z.y, acc[c].y);
+                acc[c].x = fma(-kv.y, z.y, acc[c].x);
+                acc[c].y = fma(kv.y, z.x, acc[c].y);
             }
         } else if (NC == 1) {
             const double kv = ktp[k2];
-            accA[0].x += kv * zA.x;
-            accA[0].y += kv * zA.y;
-            accB[0].x += kv * zB.x;
-            accB[0].y += kv * zB.y;
+            acc[0].x = fma(kv, z.x, acc[0].x);
+            acc[0].y = fma(kv, z.y, acc[0].y);
         } else {
-            const double2* krow = reinterpret_cast<const double2*>(ktp + k2 * NCP);
+            const double2* krow = reinterpret_cast<const double2*>(ktp + k2 * NC);
 #pragma unroll
             for (int c2 = 0; c2 < NC / 2; ++c2) {
                 const double2 kv = krow[c2];
-                accA[2 * c2].x += kv.x * zA.x;
-                accA[2 * c2].y += kv.x * zA.y;
-                accB[2 * c2].x += kv.x * zB.x;
-                accB[2 * c2].y += kv.x * zB.y;
-                accA[2 * c2 + 1].x += kv.y * zA.x;
-                accA[2 * c2 + 1].y += kv.y * zA.y;
-                accB[2 * c2 + 1].x += kv.y * zB.x;
-                accB[2 * c2 + 1].y += kv.y * zB.y;
+                acc[2 * c2].x = fma(kv.x, z.x, acc[2 * c2].x);
+                acc[2 * c2].y = fma(kv.x, z.y, acc[2 * c2].y);
+                acc[2 * c2 + 1].x = fma(kv.y, z.x, acc[2 * c2 + 1].x);
+                acc[2 * c2 + 1].y = fma(kv.y, z.y, acc[2 * c2 + 1].y);
             }
         }
     }
 }
+
+struct Mv2Smem {
+    double2* xbuf[2];
+    double2* mfs[2];
+    int* xos[2];
+    double* kt;
+    ProdS* sp;
+    long long* sbase;
+};
 
 // NC = number of register columns (>= it.nc; 1 or even), surplus columns are zero-padded in K^T
 template <int NC, bool KC>
 __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restrict__ prods,
-                                         const XRange* __restrict__ xrs_tab, const int* __restrict__ ent_col,
-                                         const double2* __restrict__ ent_val, const unsigned* __restrict__ tab_mask,
+                                         const XRange* __restrict__ xrs_tab, const int* __restrict__ ccol,
+                                         const double2* __restrict__ cval, const unsigned* __restrict__ tab_mask,
                                          const double* __restrict__ kpool, const double2* __restrict__ X,
                                          double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
-                                         int s0, const int* __restrict__ active, double* kt, double2* xbuf0,
-                                         double2* xbuf1) {
+                                         int s0, const int* __restrict__ active, const Mv2Smem& sm,
+                                         const double* __restrict__ scale, int scale_stride,
+                                         double2* __restrict__ pdot, int npart, int item_index) {
     constexpr int KW = KC ? 2 : 1;                       // doubles per K element
-    const int nsl = 2 * it.pairs;
-    const int pair = threadIdx.x / it.nrows;
-    const int rl = threadIdx.x - pair * it.nrows;
-    const int sA = s0 + 2 * pair, sB = sA + 1;
-    const bool vA = pair < it.pairs && sA < nstates && (active == nullptr || active[sA]);
-    const bool vB = pair < it.pairs && sB < nstates && (active == nullptr || active[sB]);
-    const bool work = vA || vB;
+    const int sl = threadIdx.x / it.nrows;
+    const int rl = threadIdx.x - sl * it.nrows;
+    const int st = s0 + sl;
+    const bool work = sl < it.nst && st < nstates && (active == nullptr || active[st]);
     const int np = it.p_end - it.p_begin;
+    if (__syncthreads_or(work) == 0) return;             // every state of the tile has converged
 
-    if (np > 0) mv2_stage(xbuf0, prods[it.p_begin], xrs_tab[it.xr_off], X, ldx, s0, nsl, active, nstates);
+    // ---- product descriptors and state base offsets -> shared memory
+    for (int ip = threadIdx.x; ip < np; ip += MV2_THREADS) {
+        const ProdD pr = prods[it.p_begin + ip];
+        const XRange xr = xrs_tab[it.xr_off + ip];
+        ProdS d;
+        d.ket_off = pr.ket_off + (long long)xr.c_lo * pr.dk2;
+        d.ent_off = pr.ent_off;
+        d.dk2 = pr.dk2;
+        d.nnz = min(__popc(tab_mask[pr.tab]), MV2_NDMAX);   // diagonals that survived the field contraction
+        d.c_lo = xr.c_lo;
+        d.nr = xr.nr;
+        d.xrs = pr.dk2 | 1;
+        d.pad0 = d.pad1 = d.pad2 = 0;
+        sm.sp[ip] = d;
+    }
+    if (threadIdx.x < it.nst) {
+        const int s = s0 + threadIdx.x;
+        sm.sbase[threadIdx.x] = (s < nstates && (active == nullptr || active[s])) ? (long long)s * ldx : -1;
+    }
+    __syncthreads();
+    if (np > 0) mv2_stage(sm.xbuf[0], sm.mfs[0], sm.xos[0], sm.sp[0], it, X, sm.sbase, cval, ccol);
     cp_async_commit();
     // ---- K^T of every product of the item -> shared memory: kt[p][k2][NC]
     {
         int base = 0;
-        for (int p = it.p_begin; p < it.p_end; ++p) {
-            const ProdD pr = prods[p];
+        for (int ip = 0; ip < np; ++ip) {
+            const ProdD pr = prods[it.p_begin + ip];
             const int n = pr.dk2 * NC;
             for (int idx = threadIdx.x; idx < n; idx += MV2_THREADS) {
                 const int k2 = idx / NC, c = idx - k2 * NC;
                 if (KC) {
                     double2 v = make_double2(0.0, 0.0);
                     if (c < it.nc) v = reinterpret_cast<const double2*>(kpool)[pr.koff + (long long)(it.c0 + c) * pr.dk2 + k2];
-                    reinterpret_cast<double2*>(kt + base)[idx] = v;
+                    reinterpret_cast<double2*>(sm.kt + base)[idx] = v;
                 } else {
-                    kt[base + idx] = (c < it.nc) ? kpool[pr.koff + (long long)(it.c0 + c) * pr.dk2 + k2] : 0.0;
+                    sm.kt[base + idx] = (c < it.nc) ? kpool[pr.koff + (long long)(it.c0 + c) * pr.dk2 + k2] : 0.0;
                 }
             }
             base += n * KW;
         }
     }
-    double2 accA[NC], accB[NC];
+    double2 acc[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
+    for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
 
     int ktbase = 0;
     for (int ip = 0; ip < np; ++ip) {
-        const ProdD pr = prods[it.p_begin + ip];
-        const XRange xr = xrs_tab[it.xr_off + ip];
-        double2* xcur = (ip & 1) ? xbuf1 : xbuf0;
-        double2* xnext = (ip & 1) ? xbuf0 : xbuf1;
+        const int cur = ip & 1;
+        cp_async_wait<0>();
+        __syncthreads();       // product ip has landed; everyone is done with product ip-1
         if (ip + 1 < np)
-            mv2_stage(xnext, prods[it.p_begin + ip + 1], xrs_tab[it.xr_off + ip + 1], X, ldx, s0, nsl, active, nstates);
+            mv2_stage(sm.xbuf[cur ^ 1], sm.mfs[cur ^ 1], sm.xos[cur ^ 1], sm.sp[ip + 1], it, X, sm.sbase, cval, ccol);
         cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const unsigned mask = tab_mask[pr.tab];     // non-zero diagonals after the field contraction
-        if (work && mask != 0u) {
-            double2 mf[MV2_NDMAX];
-            int xo[MV2_NDMAX];
-#pragma unroll
-            for (int q = 0; q < MV2_NDMAX; ++q) { mf[q] = make_double2(0.0, 0.0); xo[q] = 0; }
-            const long long eb = pr.ent_off + (long long)(it.r0 + rl) * pr.nd;
-            const int xrs = xrs_of(pr.dk2);
-            int nnz = 0;
-#pragma unroll
-            for (int j = 0; j < MV2_NDMAX; ++j) {
-                if ((mask >> j) & 1u) {
-                    const int col = ent_col[eb + j];
-                    const double2 v = ent_val[eb + j];
-#pragma unroll
-                    for (int q = 0; q < MV2_NDMAX; ++q)
-                        if (q == nnz && col >= 0) { mf[q] = v; xo[q] = (col - xr.c_lo) * xrs; }
-                    ++nnz;
-                }
-            }
-            const double2* xa = xcur + (long long)(2 * pair) * xr.nr * xrs;
-            const double2* xb = xa + (long long)xr.nr * xrs;
-            const double* ktp = kt + ktbase;
+        const int dk2 = sm.sp[ip].dk2, nnz = sm.sp[ip].nnz;
+        if (work) {
+            const double2* xa = sm.xbuf[cur] + (long long)sl * sm.sp[ip].nr * sm.sp[ip].xrs;
+            const double2* mfs = sm.mfs[cur] + rl;
+            const int* xos = sm.xos[cur] + rl;
+            const double* ktp = sm.kt + ktbase;
             switch (nnz) {
-                case 1: mv2_inner<NC, 1, KC>(xa, xb, mf, xo, ktp, pr.dk2, accA, accB); break;
-                case 2: mv2_inner<NC, 2, KC>(xa, xb, mf, xo, ktp, pr.dk2, accA, accB); break;
-                case 3: mv2_inner<NC, 3, KC>(xa, xb, mf, xo, ktp, pr.dk2, accA, accB); break;
-                case 4: mv2_inner<NC, 4, KC>(xa, xb, mf, xo, ktp, pr.dk2, accA, accB); break;
-                default: mv2_inner<NC, 5, KC>(xa, xb, mf, xo, ktp, pr.dk2, accA, accB); break;
+                case 0: break;
+                case 1: mv2_inner<NC, 1, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
+                case 2: mv2_inner<NC, 2, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
+                case 3: mv2_inner<NC, 3, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
+                case 4: mv2_inner<NC, 4, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
+                default: mv2_inner<NC, 5, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
             }
         }
-        ktbase += pr.dk2 * NC * KW;
-        __syncthreads();   // everyone is done with xcur before it is refilled
+        ktbase += dk2 * NC * KW;
     }
     cp_async_wait<0>();
-    if (vA) {
-        double2* y = Y + (long long)sA * ldy + it.bra_off + (long long)(it.r0 + rl) * it.dk1 + it.c0;
+    // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
+    //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
+    double pre = 0.0, pim = 0.0;
+    if (work) {
+        const long long row_off = it.bra_off + (long long)(it.r0 + rl) * it.dk1 + it.c0;
+        if (scale != nullptr) {
+            const double sc = scale[(long long)st * scale_stride];
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            if (c < it.nc) y[c] = accA[c];
+            for (int c = 0; c < NC; ++c) { acc[c].x *= sc; acc[c].y *= sc; }
+        }
+        if (Y != nullptr) {
+            double2* y = Y + (long long)st * ldy + row_off;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < it.nc) y[c] = acc[c];
+        }
+        if (pdot != nullptr) {
+            const double2* x = X + (long long)st * ldx + row_off;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < it.nc) {
+                    const double2 v = x[c];
+                    pre += acc[c].x * v.x + acc[c].y * v.y;
+                    pim += acc[c].x * v.y - acc[c].y * v.x;
+                }
+        }
     }
-    if (vB) {
-        double2* y = Y + (long long)sB * ldy + it.bra_off + (long long)(it.r0 + rl) * it.dk1 + it.c0;
+    if (pdot != nullptr) {
+        __syncthreads();                        // shared buffers are free again
+        double* red = reinterpret_cast<double*>(sm.xbuf[0]);
+        red[threadIdx.x] = pre;
+        red[MV2_THREADS + threadIdx.x] = pim;
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int s = warp; s < it.nst; s += MV2_THREADS / 32) {
+            const int sg = s0 + s;
+            if (sg >= nstates || (active != nullptr && !active[sg])) continue;
+            double a = 0.0, b = 0.0;
+            for (int r = lane; r < it.nrows; r += 32) {
+                a += red[s * it.nrows + r];
+                b += red[MV2_THREADS + s * it.nrows + r];
+            }
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            if (c < it.nc) y[c] = accB[c];
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_down_sync(0xffffffffu, a, o);
+                b += __shfl_down_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) pdot[(long long)sg * npart + item_index] = make_double2(a, b);
+        }
     }
 }
 
@@ -224,24 +291,33 @@ template <bool KC>
 __global__ void __launch_bounds__(MV2_THREADS, 2)
 k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ items,
                const ProdD* __restrict__ prods, const XRange* __restrict__ xrs_tab,
-               const int* __restrict__ ent_col, const double2* __restrict__ ent_val,
+               const int* __restrict__ ccol, const double2* __restrict__ cval,
                const unsigned* __restrict__ tab_mask, const double* __restrict__ kpool,
                const double2* __restrict__ X, double2* __restrict__ Y, long long ldx, long long ldy,
-               int nstates, const int* __restrict__ active, int kt_doubles, int xbuf_elems) {
+               int nstates, const int* __restrict__ active, int np_max, int kt_doubles, int xbuf_elems,
+               int mf_elems, const double* __restrict__ scale, int scale_stride, double2* __restrict__ pdot,
+               int npart) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* xbuf0 = reinterpret_cast<double2*>(smem_raw);
-    double2* xbuf1 = xbuf0 + xbuf_elems;
-    double* kt = reinterpret_cast<double*>(xbuf1 + xbuf_elems);
+    Mv2Smem sm;
+    sm.xbuf[0] = reinterpret_cast<double2*>(smem_raw);
+    sm.xbuf[1] = sm.xbuf[0] + xbuf_elems;
+    sm.mfs[0] = sm.xbuf[1] + xbuf_elems;
+    sm.mfs[1] = sm.mfs[0] + mf_elems;
+    sm.kt = reinterpret_cast<double*>(sm.mfs[1] + mf_elems);
+    sm.sp = reinterpret_cast<ProdS*>(sm.kt + kt_doubles);
+    sm.sbase = reinterpret_cast<long long*>(sm.sp + np_max);
+    sm.xos[0] = reinterpret_cast<int*>(sm.sbase + MV2_SMAX);
+    sm.xos[1] = sm.xos[0] + mf_elems;
     const Unit2D u = units[blockIdx.x];
     const Item2D it = items[u.item];
 #define RMB_CASE(N)                                                                                        \
     case N:                                                                                                \
-        mv2_body<N, KC>(it, prods, xrs_tab, ent_col, ent_val, tab_mask, kpool, X, Y, ldx, ldy, nstates,    \
-                        u.s0, active, kt, xbuf0, xbuf1);                                                   \
+        mv2_body<N, KC>(it, prods, xrs_tab, ccol, cval, tab_mask, kpool, X, Y, ldx, ldy, nstates,          \
+                        u.s0, active, sm, scale, scale_stride, pdot, npart, u.item);                       \
         break;
     switch (it.nc == 1 ? 1 : (it.nc + 1) & ~1) {
         RMB_CASE(1) RMB_CASE(2) RMB_CASE(4) RMB_CASE(6) RMB_CASE(8)
-        RMB_CASE(10) RMB_CASE(12) RMB_CASE(14) RMB_CASE(16)
+        RMB_CASE(10) RMB_CASE(12)
         default: break;
     }
 #undef RMB_CASE
