@@ -56,6 +56,7 @@ void rmb_operator_destroy(rmb_operator* op) {
     if (!op) return;
     cudaFree(op->d_prods);
     cudaFree(op->d_items);
+    cudaFree(op->d_pmap);
     cudaFree(op->d_items2);
     cudaFree(op->d_xranges);
     cudaFree(op->d_units);
@@ -124,6 +125,27 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     RMB_CUDA(cudaDeviceGetAttribute(&op->num_sms, cudaDevAttrMultiProcessorCount, op->device));
     op->nblocks = d->nblocks;
     op->n = d->blk_off[d->nblocks];
+    // internal (padded) layout: every (J,sym) block stores rows of (dim_k | 1) elements, so that rows
+    // staged into shared memory are contiguous in HBM and row-strided reads are bank-conflict free
+    std::vector<long long> poff(d->nblocks + 1, 0);
+    for (int b = 0; b < d->nblocks; ++b)
+        poff[b + 1] = poff[b] + (long long)d->blk_dm[b] * (d->blk_dk[b] | 1);
+    op->np = poff[d->nblocks];
+    if (op->np >= (1LL << 31)) {
+        set_error("Hilbert space too large for 32-bit internal indices");
+        return RMB_ERR_INVALID;
+    }
+    {
+        std::vector<int> pmap((size_t)op->n);
+        for (int b = 0; b < d->nblocks; ++b) {
+            const int dk = d->blk_dk[b], dkp = dk | 1;
+            for (int r = 0; r < d->blk_dm[b]; ++r)
+                for (int c = 0; c < dk; ++c)
+                    pmap[(size_t)(d->blk_off[b] + (long long)r * dk + c)] = (int)(poff[b] + (long long)r * dkp + c);
+        }
+        int rc0 = upload(&op->d_pmap, pmap.data(), pmap.size());
+        if (rc0) return rc0;
+    }
     for (int b = 0; b < d->nblocks; ++b) {
         if (d->blk_off[b + 1] - d->blk_off[b] != (long long)d->blk_dm[b] * d->blk_dk[b]) {
             set_error("block offsets inconsistent with dim_m*dim_k");
@@ -209,7 +231,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     for (size_t i = 0; i < perm.size(); ++i) {
         const HProd& h = hp[perm[i]];
         ProdD& pr = op->h_prods[i];
-        pr.ket_off = d->blk_off[h.ket];
+        pr.ket_off = poff[h.ket];
         pr.koff = h.koff;
         pr.ent_off = h.ent_off;
         pr.dk2 = d->blk_dk[h.ket];
@@ -275,7 +297,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 for (int c0 = 0; c0 < dk1; c0 += MV2_NCMAX)
                     for (int r0 = 0; r0 < dm1; r0 += nr_t) {
                         Item2D it;
-                        it.bra_off = d->blk_off[b];
+                        it.bra_off = poff[b];
                         it.dk1 = dk1;
                         it.dm1 = dm1;
                         it.r0 = r0;
@@ -323,7 +345,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         for (int c0 = 0; c0 < dk1; c0 += ncols_t)
             for (int r0 = 0; r0 < dm1; r0 += nrows_t) {
                 ItemD it;
-                it.bra_off = d->blk_off[b];
+                it.bra_off = poff[b];
                 it.dk1 = dk1;
                 it.r0 = r0;
                 it.nrows = std::min(nrows_t, dm1 - r0);
@@ -592,11 +614,12 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     for (auto* s : op->slabs) cudaFree(s);
     op->slabs.clear();
     op->slab_ptrs_uploaded = 0;
-    op->nchunk = nchunks(op->n);
+    op->nchunk = nchunks(op->np);
     int rc;
-    const size_t vec = (size_t)cap * (size_t)op->n;
+    const size_t vec = (size_t)cap * (size_t)op->np;
     const size_t np = (size_t)std::max(op->nchunk, op->nitems2);
     if ((rc = ensure(&op->d_w, vec))) return rc;
+    RMB_CUDA(cudaMemset(op->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
     if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
     if ((rc = ensure(&op->d_beta, (size_t)cap * (maxorder + 1)))) return rc;
     if ((rc = ensure(&op->d_rinv, (size_t)cap * (maxorder + 1)))) return rc;
@@ -624,7 +647,8 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
 static int ensure_slab(rmb_operator* op, int k, cudaStream_t st) {
     while ((int)op->slabs.size() <= k) {
         cplx* p = nullptr;
-        RMB_CUDA(cudaMalloc((void**)&p, (size_t)op->ws_states * (size_t)op->n * sizeof(cplx)));
+        RMB_CUDA(cudaMalloc((void**)&p, (size_t)op->ws_states * (size_t)op->np * sizeof(cplx)));
+        RMB_CUDA(cudaMemsetAsync(p, 0, (size_t)op->ws_states * (size_t)op->np * sizeof(cplx), st));
         op->slabs.push_back(p);
     }
     if (op->slab_ptrs_cap < (int)op->slabs.size() || !op->d_slab_ptrs) {
@@ -654,9 +678,10 @@ static int ensure_slab(rmb_operator* op, int k, cudaStream_t st) {
 static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol,
                          int maxorder, const cplx* ph, int* orders_host, cudaStream_t st,
                          bool* hit_maxorder) {
-    const long long n = op->n;
+    const long long n = op->n, np = op->np;
     const int nch = op->nchunk;
-    const dim3 vgrid((unsigned)nch, (unsigned)B);
+    const dim3 vgrid((unsigned)nch, (unsigned)B);          // padded vectors
+    const dim3 ugrid((unsigned)nchunks(n), (unsigned)B);   // user-layout vectors
     const int ts = op->ws_maxorder, bs = op->ws_maxorder + 1;
     const bool fused = fused_dot(op);
     const int npart = dot_parts(op);
@@ -665,7 +690,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
     k_init_states<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, op->d_order, op->d_rinv,
                                                                op->d_beta, bs, (int)B);
-    k_phase_init<<<vgrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], n, n);
+    k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], np, n, op->d_pmap);
     op->n_launches += 2;
     int k = 0, last = -1;
     std::vector<long long> act_hist;
@@ -679,22 +704,22 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             ep.pdot = op->d_pdot;
             ep.npart = npart;
         }
-        if ((rc = launch_matvec(op, Vk, op->d_w, B, n, n, op->d_active, st, ep))) return rc;
+        if ((rc = launch_matvec(op, Vk, op->d_w, B, np, np, op->d_active, st, ep))) return rc;
         if (!fused) {
             // some bra blocks went through the scalar kernel, which has no epilogue: scale the product
             // (w = rinv_k * H slab_k) and form the partial dots in separate passes
-            k_scale_rows<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, n, n, op->d_rinv + k, bs, op->d_active);
-            k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, n, n, op->d_pdot, npart, op->d_active);
+            k_scale_rows<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, np, np, op->d_rinv + k, bs, op->d_active);
+            k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, np, np, op->d_pdot, npart, op->d_active);
             op->n_launches += 2;
         }
         k_small_a<<<(unsigned)B, 32, 0, st>>>(op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, ts, bs, k,
                                               fac, op->d_ccur, op->d_ceff, op->d_dc, op->d_active);
-        k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, n, n, op->d_alpha, op->d_beta,
+        k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, np, np, op->d_alpha, op->d_beta,
                                                     op->d_rinv, op->d_dc, ts, bs, k, op->d_pnrm, op->d_pconv,
                                                     nch, op->d_active);
         k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_pnrm, op->d_pconv, nch, op->d_beta, op->d_rinv, bs, k,
                                                        tol, maxorder, op->d_active, op->d_order, op->d_ctrl,
-                                                       op->d_slab_ptrs, n, n);
+                                                       op->d_slab_ptrs, np, n, op->d_pmap);
         op->n_launches += 3;
         op->n_iterations++;
         RMB_CUDA(cudaMemcpyAsync(op->h_ctrl + 4 * k, op->d_ctrl + 4 * k, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -712,7 +737,8 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
         }
     }
     (void)last;
-    k_combine<<<vgrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, n, n, op->d_ceff, ts, op->d_order, ph, psi, ld);
+    k_combine<<<ugrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, np, n, op->d_ceff, ts, op->d_order, ph, psi, ld,
+                                             op->d_pmap);
     op->n_launches++;
     RMB_CUDA(cudaGetLastError());
     // state-matvecs actually performed: all states in iteration 0, the survivors of k-1 in iteration k
@@ -756,10 +782,10 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         if (budget <= 0) {
             size_t fr = 0, tot = 0;
             RMB_CUDA(cudaMemGetInfo(&fr, &tot));
-            long long held = (long long)(op->slabs.size() + 1) * op->ws_states * n * (long long)sizeof(cplx);
+            long long held = (long long)(op->slabs.size() + 1) * op->ws_states * op->np * (long long)sizeof(cplx);
             budget = (long long)(0.4 * (double)(fr + (size_t)held));
         }
-        const long long per_state = 16LL * n * (long long)sizeof(cplx);
+        const long long per_state = 16LL * op->np * (long long)sizeof(cplx);
         bc = std::max(1LL, std::min({(long long)nstates, budget / per_state, 65535LL}));
         if (bc <= op->ws_states) bc = op->ws_states;
         op->ws_budget_fixed = true;   // the size is settled for this handle unless the budget is changed
@@ -783,6 +809,16 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
     return RMB_OK;
 }
 
+// scratch for the entry points that take user-layout vectors: one padded slab + the product vector
+static int scratch_for(rmb_operator* op, long long nstates, cudaStream_t st) {
+    int rc;
+    if (op->ws_states == 0) {
+        const long long cap = std::max<long long>(1, (1LL << 30) / (op->np * (long long)sizeof(cplx)));
+        if ((rc = ensure_workspace(op, std::min<long long>({nstates, cap, 65535LL}), 1))) return rc;
+    }
+    return ensure_slab(op, 0, st);
+}
+
 }  // namespace rmb
 
 extern "C" {
@@ -795,9 +831,23 @@ int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t
     }
     int rc = check_field(op);
     if (rc) return rc;
-    rc = launch_matvec(op, (const cplx*)x_dev, (cplx*)y_dev, nstates, ld, ld, nullptr, (cudaStream_t)stream);
-    if (rc == RMB_OK) op->n_state_matvecs += nstates;
-    return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nstates == 0) return RMB_OK;
+    if ((rc = scratch_for(op, nstates, st))) return rc;
+    const long long bc = op->ws_states, n = op->n, np = op->np;
+    for (long long s0 = 0; s0 < nstates; s0 += bc) {
+        const long long b = std::min(bc, (long long)nstates - s0);
+        const dim3 ugrid((unsigned)nchunks(n), (unsigned)b);
+        // user layout -> padded scratch, product, back
+        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)x_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
+                                                    op->d_pmap);
+        if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st))) return rc;
+        k_unpad<<<ugrid, VEC_THREADS, 0, st>>>(op->d_w, np, (cplx*)y_dev + s0 * ld, ld, n, op->d_pmap);
+        op->n_launches += 2;
+        op->n_state_matvecs += b;
+    }
+    RMB_CUDA(cudaGetLastError());
+    return RMB_OK;
 }
 
 int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld, double fac_re,
@@ -855,30 +905,30 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
     int rc = check_field(op);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const long long n = op->n;
+    const long long n = op->n, np = op->np;
     if (nstates == 0) return RMB_OK;
-    if (op->ws_states == 0) {
-        // product vector only: at most 1 GiB of scratch
-        const long long cap = std::max<long long>(1, (1LL << 30) / (n * (long long)sizeof(cplx)));
-        if ((rc = ensure_workspace(op, std::min<long long>({(long long)nstates, cap, 65535LL}), 1))) return rc;
-    }
+    if ((rc = scratch_for(op, nstates, st))) return rc;
     const long long bc = op->ws_states;
     const int nch = op->nchunk;
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, (long long)nstates - s0);
-        const cplx* psi = (const cplx*)psi_dev + s0 * ld;
+        const dim3 ugrid((unsigned)nchunks(n), (unsigned)b);
+        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
+                                                    op->d_pmap);
+        op->n_launches++;
         if (fused_dot(op)) {
             // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
             // the product vector itself is never written
             MvEpilogue ep;
             ep.pdot = op->d_pdot;
             ep.npart = op->nitems2;
-            if ((rc = launch_matvec(op, psi, nullptr, b, ld, n, nullptr, st, ep))) return rc;
+            if ((rc = launch_matvec(op, op->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, op->nitems2, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;
         } else {
-            if ((rc = launch_matvec(op, psi, op->d_w, b, ld, n, nullptr, st))) return rc;
-            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(psi, ld, op->d_w, n, n, op->d_pdot, nch);
+            if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st))) return rc;
+            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(op->slabs[0], np, op->d_w, np, np,
+                                                                             op->d_pdot, nch);
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, nch, (cplx*)expval_dev + s0, 1.0);
             op->n_launches += 2;
         }

@@ -62,6 +62,8 @@ struct rmb_operator {
     int device = 0;
     int num_sms = 148;
     long long n = 0;                 // Hilbert-space dimension
+    long long np = 0;                // padded length of the internal vectors (rows of dim_k | 1 elements)
+    int* d_pmap = nullptr;           // [n] position of element i in the padded layout
     int nblocks = 0;
     int nprod = 0;
     int nitems = 0;

@@ -166,7 +166,7 @@ k_matvec_scalar(const ItemD* __restrict__ items, const ProdD* __restrict__ prods
                 const cplx* xs = X + (long long)st * ldx + pr.ket_off + k2;
                 for (int j = 0; j < pr.nd; ++j) {
                     const int col = ent_col[eb + j];
-                    if (col >= 0) cfma(z, ent_val[eb + j], xs[(long long)col * pr.dk2]);
+                    if (col >= 0) cfma(z, ent_val[eb + j], xs[(long long)col * (pr.dk2 | 1)]);
                 }
             }
             zs[s * zstride + rem] = z;
@@ -198,7 +198,7 @@ k_matvec_scalar(const ItemD* __restrict__ items, const ProdD* __restrict__ prods
         if (threadIdx.x + i * MV_THREADS < total) {
             const int st = s0 + o_s[i];
             if (active == nullptr || active[st])
-                Y[(long long)st * ldy + it.bra_off + (long long)(it.r0 + o_r[i]) * it.dk1 + it.c0 + o_c[i]] = acc[i];
+                Y[(long long)st * ldy + it.bra_off + (long long)(it.r0 + o_r[i]) * (it.dk1 | 1) + it.c0 + o_c[i]] = acc[i];
         }
     }
 }
@@ -212,10 +212,11 @@ k_matvec_scalar(const ItemD* __restrict__ items, const ProdD* __restrict__ prods
 // normalisation pass over the vector.
 // ------------------------------------------------------------------------------------------
 
-// V0 = psi * ph  (tdse.py:375), or a plain copy when ph == nullptr
+// V0 = psi * ph  (tdse.py:375), or a plain copy when ph == nullptr; scatters into the padded layout
+// (pad elements of every internal vector are zero at all times)
 __global__ void __launch_bounds__(VEC_THREADS)
 k_phase_init(const cplx* __restrict__ psi, long long ld, const cplx* __restrict__ ph,
-             cplx* __restrict__ V0, long long ldv, long long n) {
+             cplx* __restrict__ V0, long long ldv, long long n, const int* __restrict__ pmap) {
     const long long base = (long long)blockIdx.x * VEC_CHUNK;
     const long long s = blockIdx.y;
 #pragma unroll
@@ -224,8 +225,21 @@ k_phase_init(const cplx* __restrict__ psi, long long ld, const cplx* __restrict_
         if (x < n) {
             cplx v = psi[s * ld + x];
             if (ph) v = cmul(v, ph[x]);
-            V0[s * ldv + x] = v;
+            V0[s * ldv + pmap[x]] = v;
         }
+    }
+}
+
+// padded -> user layout
+__global__ void __launch_bounds__(VEC_THREADS)
+k_unpad(const cplx* __restrict__ src, long long ldv, cplx* __restrict__ dst, long long ld, long long n,
+        const int* __restrict__ pmap) {
+    const long long base = (long long)blockIdx.x * VEC_CHUNK;
+    const long long s = blockIdx.y;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_THREAD; ++i) {
+        const long long x = base + threadIdx.x + i * VEC_THREADS;
+        if (x < n) dst[s * ld + x] = src[s * ldv + pmap[x]];
     }
 }
 
@@ -440,7 +454,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_small_b(const double* __restrict__ pnrm, const double* __restrict__ pconv, int nchunk,
           double* __restrict__ beta, double* __restrict__ rinv, int bstride, int k, double tol, int maxorder,
           int* __restrict__ active, int* __restrict__ order, int* __restrict__ ctrl,
-          cplx* const* __restrict__ slabs, long long ldv, long long n) {
+          cplx* const* __restrict__ slabs, long long ldv, long long n, const int* __restrict__ pmap) {
     __shared__ double sm[VEC_THREADS / 32];
     __shared__ double2 bc;
     __shared__ int s_fallback;
@@ -473,16 +487,17 @@ k_small_b(const double* __restrict__ pnrm, const double* __restrict__ pconv, int
     }
     __syncthreads();
     if (!s_fallback) return;
-    // ---- Gram-Schmidt of ones against V_0..V_k (V_j = slab_j * rinv_j)
+    // ---- Gram-Schmidt of ones against V_0..V_k (V_j = slab_j * rinv_j); pad elements stay zero
     cplx* v = slabs[k + 1] + s * ldv;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(1.0, 0.0);
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[pmap[x]] = make_double2(1.0, 0.0);
     __syncthreads();
     for (int j = 0; j <= k; ++j) {
         const cplx* vj = slabs[j] + s * ldv;
         const double rj = rinv[s * bstride + j];
         double pr = 0, pi = 0;   // proj = vdot(V_j, v) = sum conj(V_j) * v
         for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
-            const cplx a = make_double2(vj[x].x * rj, vj[x].y * rj), b = v[x];
+            const int xp = pmap[x];
+            const cplx a = make_double2(vj[xp].x * rj, vj[xp].y * rj), b = v[xp];
             pr += a.x * b.x + a.y * b.y;
             pi += a.x * b.y - a.y * b.x;
         }
@@ -492,25 +507,29 @@ k_small_b(const double* __restrict__ pnrm, const double* __restrict__ pconv, int
         __syncthreads();
         const cplx proj = bc;
         for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
-            const cplx a = make_double2(vj[x].x * rj, vj[x].y * rj);
-            v[x] = csub(v[x], cmul(proj, a));
+            const int xp = pmap[x];
+            const cplx a = make_double2(vj[xp].x * rj, vj[xp].y * rj);
+            v[xp] = csub(v[xp], cmul(proj, a));
         }
         __syncthreads();
     }
     double nr = 0;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) nr += cabs2(v[x]);
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) nr += cabs2(v[pmap[x]]);
     nr = block_sum<VEC_THREADS>(nr, sm);
     if (threadIdx.x == 0) bc = make_double2(sqrt(nr), 0.0);
     __syncthreads();
     const double nv = bc.x;
-    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) v[x] = make_double2(v[x].x / nv, v[x].y / nv);
+    for (long long x = threadIdx.x; x < n; x += VEC_THREADS) {
+        const int xp = pmap[x];
+        v[xp] = make_double2(v[xp].x / nv, v[xp].y / nv);
+    }
 }
 
 // psi = ph * sum_{i<=order} c_i V_i   (tdse.py:475,394), c_i V_i = ceff_i * slab_i
 __global__ void __launch_bounds__(VEC_THREADS)
 k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* __restrict__ ceff,
           int tstride, const int* __restrict__ order, const cplx* __restrict__ ph,
-          cplx* __restrict__ psi, long long ld) {
+          cplx* __restrict__ psi, long long ld, const int* __restrict__ pmap) {
     __shared__ double2 sc[MAX_ORDER_SMEM];
     const long long s = blockIdx.y;
     const int k = order[s];
@@ -520,13 +539,19 @@ k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cpl
     cplx u[VEC_PER_THREAD];
 #pragma unroll
     for (int i = 0; i < VEC_PER_THREAD; ++i) u[i] = make_double2(0.0, 0.0);
+    int xp[VEC_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < VEC_PER_THREAD; ++i) {
+        const long long x = base + threadIdx.x + i * VEC_THREADS;
+        xp[i] = x < n ? pmap[x] : 0;
+    }
     for (int j = 0; j <= k; ++j) {
         const cplx* vj = slabs[j] + s * ldv;
         const cplx c = sc[j];
 #pragma unroll
         for (int i = 0; i < VEC_PER_THREAD; ++i) {
             const long long x = base + threadIdx.x + i * VEC_THREADS;
-            if (x < n) cfma(u[i], c, vj[x]);
+            if (x < n) cfma(u[i], c, vj[xp[i]]);
         }
     }
 #pragma unroll

@@ -52,28 +52,19 @@ __device__ __forceinline__ void mv2_stage(double2* xb, double2* mfs, int* xos, c
                                           const Item2D& it, const double2* __restrict__ X,
                                           const long long* __restrict__ sbase, const double2* __restrict__ cval,
                                           const int* __restrict__ ccol) {
-    const int per_state = pr.nr * pr.dk2;
+    // the internal vectors store rows of (dim_k | 1) elements, so the ket rows are one contiguous run
+    const int per_state = pr.nr * pr.xrs;
     const unsigned dst0 = (unsigned)__cvta_generic_to_shared(xb);
-    const unsigned sstride = (unsigned)(pr.nr * pr.xrs) * 16u;
+    const unsigned sstride = (unsigned)per_state * 16u;
     const double2* src0 = X + pr.ket_off;
-    // element e = rl * dk2 + k2 advances by MV2_THREADS per iteration
-    const float inv = 1.0f / (float)pr.dk2;
-    int rl = __float2int_rz(((float)threadIdx.x + 0.5f) * inv);
-    int k2 = threadIdx.x - rl * pr.dk2;
-    const int q256 = __float2int_rz(((float)MV2_THREADS + 0.5f) * inv);
-    const int r256 = MV2_THREADS - q256 * pr.dk2;
     for (int e = threadIdx.x; e < per_state; e += MV2_THREADS) {
-        const unsigned off = (unsigned)(rl * pr.xrs + k2) * 16u;
         const double2* src = src0 + e;
 #pragma unroll 4
         for (int s = 0; s < it.nst; ++s) {
             const long long sb = sbase[s];
             if (sb >= 0)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + s * sstride + off), "l"(src + sb));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + s * sstride + e * 16u), "l"(src + sb));
         }
-        k2 += r256;
-        rl += q256;
-        if (k2 >= pr.dk2) { k2 -= pr.dk2; ++rl; }
     }
     // MF diagonals: mfs[q][rl], xos[q][rl]
     const int n = pr.nnz * it.nrows;
@@ -169,7 +160,7 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
         const ProdD pr = prods[it.p_begin + ip];
         const XRange xr = xrs_tab[it.xr_off + ip];
         ProdS d;
-        d.ket_off = pr.ket_off + (long long)xr.c_lo * pr.dk2;
+        d.ket_off = pr.ket_off + (long long)xr.c_lo * (pr.dk2 | 1);
         d.ent_off = pr.ent_off;
         d.dk2 = pr.dk2;
         d.nnz = min(__popc(tab_mask[pr.tab]), MV2_NDMAX);   // diagonals that survived the field contraction
@@ -239,7 +230,7 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
     //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
     double pre = 0.0, pim = 0.0;
     if (work) {
-        const long long row_off = it.bra_off + (long long)(it.r0 + rl) * it.dk1 + it.c0;
+        const long long row_off = it.bra_off + (long long)(it.r0 + rl) * (it.dk1 | 1) + it.c0;
         if (scale != nullptr) {
             const double sc = scale[(long long)st * scale_stride];
 #pragma unroll
