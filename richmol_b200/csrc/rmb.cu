@@ -62,8 +62,7 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_units);
     cudaFree(op->d_ent_col);
     cudaFree(op->d_ent_val);
-    cudaFree(op->d_ent_cval);
-    cudaFree(op->d_ent_ccol);
+    cudaFree(op->d_ent_cent);
     cudaFree(op->d_ent_tab);
     cudaFree(op->d_tab_off);
     cudaFree(op->d_tab_nd);
@@ -221,6 +220,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         if (rc) return rc;
     }
     op->nent = (long long)ent_col.size();
+    tab_off.push_back((int)ent_col.size());   // extent of the last table (tab_off has ntab + 1 entries)
     op->nprod = (int)hp.size();
     // ---- sort products by bra block (stable: keeps part / input order inside a block)
     std::vector<int> perm(hp.size());
@@ -247,6 +247,23 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     const int max_out = MV_THREADS * MV_ACC / S;   // outputs per state and CTA
     int zstride = 1;
     double flops = 0, opbytes = 0;
+    // diagonal span (max - min of col - row) of every product's MF table: rows staged = tile rows + span
+    std::vector<int> h_span(op->h_prods.size(), 0);
+    for (size_t p = 0; p < op->h_prods.size(); ++p) {
+        const ProdD& q = op->h_prods[p];
+        const long long nrow = (long long)(tab_off[q.tab + 1] - tab_off[q.tab]) / q.nd;
+        int lo = 1 << 30, hi = -(1 << 30);
+        for (long long r = 0; r < nrow; ++r)
+            for (int j = 0; j < q.nd; ++j) {
+                const int col = ent_col[q.ent_off + r * q.nd + j];
+                if (col >= 0) { lo = std::min(lo, col - (int)r); hi = std::max(hi, col - (int)r); }
+            }
+        h_span[p] = hi >= lo ? hi - lo : 0;
+    }
+    auto item_smem = [](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod) {
+        return (size_t)MV2_STAGES * xbuf_elems * 16 + (size_t)MV2_STAGES * MV2_NDMAX * nrows * sizeof(MfEntry) +
+               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + MV2_SMAX * 8 + 2 * MV2_STAGES * 8 + 128;
+    };
     const char* force = getenv("RMB_MATVEC");
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
@@ -270,25 +287,27 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         if (fast) {
             int best_nt = 0, best_nst = 0;
             double best_util = -1;
-            const int nt0 = (dm1 + MV2_THREADS - 1) / MV2_THREADS;
+            const int nt0 = (dm1 + MV2_CONSUMERS - 1) / MV2_CONSUMERS;
             for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
                 const int nr = (dm1 + nt - 1) / nt;
-                int nst = std::min(MV2_SMAX, MV2_THREADS / nr);
-                // shared memory: K^T of all products + two ket-row buffers + descriptors
+                int nst = std::min(MV2_SMAX, MV2_CONSUMERS / nr);
+                // shared memory of the item (exactly what the kernel carves): staging buffers for the ket
+                // rows and MF diagonals, K^T of all products, descriptors, state offsets, barriers
                 auto need = [&](int nst_) {
-                    size_t kt = 0, xb = 0;
+                    size_t kt = 0, xb = 256;
+                    const int nc0 = std::min(dk1, MV2_NCMAX);
+                    const int ncp = nc0 == 1 ? 1 : ((nc0 + 1) & ~1);
                     for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
                         const ProdD& q = op->h_prods[p];
-                        const int nc0 = std::min(dk1, MV2_NCMAX);
-                        const int ncp = nc0 == 1 ? 1 : ((nc0 + 1) & ~1);
-                        kt += (size_t)q.dk2 * ncp * (kc ? 2 : 1) * 8 + sizeof(ProdS);
-                        xb = std::max(xb, (size_t)nst_ * std::min(q.dm2, nr + 2 * q.nd) * (q.dk2 | 1) * 16);
+                        kt += (size_t)q.dk2 * ncp * (kc ? 2 : 1);
+                        xb = std::max(xb, (size_t)nst_ * std::min(q.dm2, nr + h_span[p]) * (q.dk2 | 1));
                     }
-                    return kt + 2 * xb + (size_t)2 * MV2_NDMAX * nr * 20 + MV2_SMAX * 8 + 64;
+                    kt = (kt + 1) & ~(size_t)1;
+                    return item_smem(xb, nr, kt, bra_begin[b + 1] - bra_begin[b]);
                 };
                 while (nst > 1 && need(nst) > smem_budget) --nst;
                 if (need(nst) > smem_budget) continue;
-                const double util = (double)nr * nst / MV2_THREADS * ((double)dm1 / (nr * nt));
+                const double util = (double)nr * nst / MV2_CONSUMERS * ((double)dm1 / (nr * nt));
                 if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_nst = nst; }
             }
             if (best_nt == 0) fast = false;
@@ -310,6 +329,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         it.xr_off = (int)xranges.size();
                         const int ncp = it.nc == 1 ? 1 : ((it.nc + 1) & ~1);
                         int ktd = 0;
+                        int xbe = 256;
                         for (int p = it.p_begin; p < it.p_end; ++p) {
                             const ProdD& q = op->h_prods[p];
                             ktd += q.dk2 * ncp * (kc ? 2 : 1);
@@ -323,12 +343,13 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             xr.c_lo = hi < 0 ? 0 : lo;
                             xr.nr = hi < 0 ? 0 : hi - lo + 1;
                             xranges.push_back(xr);
-                            op->xbuf_elems = std::max({op->xbuf_elems, it.nst * xr.nr * (q.dk2 | 1), 256});
+                            xbe = std::max(xbe, it.nst * xr.nr * (q.dk2 | 1));
                         }
-                        it.kt_total = ktd;
-                        op->kt_doubles = std::max(op->kt_doubles, (ktd + 1) & ~1);
-                        op->np_max = std::max(op->np_max, it.p_end - it.p_begin);
-                        op->mf_elems = std::max(op->mf_elems, MV2_NDMAX * it.nrows);
+                        it.kt_total = (ktd + 1) & ~1;
+                        it.xbuf_elems = xbe;
+                        it.pad = 0;
+                        op->matvec2_smem = std::max(op->matvec2_smem,
+                                                    item_smem((size_t)xbe, it.nrows, (size_t)it.kt_total, it.p_end - it.p_begin));
                         items2.push_back(it);
                     }
                 continue;
@@ -375,8 +396,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     }
     op->nitems2 = (int)items2.size();
     for (auto& it : items2) op->h_item2_states.push_back(it.nst);
-    op->matvec2_smem = (size_t)op->kt_doubles * 8 + (size_t)2 * op->xbuf_elems * 16 + (size_t)op->np_max * sizeof(ProdS) +
-                       (size_t)2 * op->mf_elems * 20 + MV2_SMAX * 8;
+
     opbytes += 20.0 * (double)op->nent;   // MF values + column indices
     op->flops_per_state = flops;
     op->op_bytes = opbytes;
@@ -408,12 +428,9 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     }
     if ((rc = upload(&op->d_ent_col, ent_col.data(), ent_col.size()))) return rc;
     if ((rc = upload<cplx>(&op->d_ent_val, nullptr, (size_t)op->nent))) return rc;
-    if ((rc = upload<cplx>(&op->d_ent_cval, nullptr, (size_t)op->nent))) return rc;
-    if ((rc = upload<int>(&op->d_ent_ccol, nullptr, (size_t)op->nent))) return rc;
-    RMB_CUDA(cudaMemset(op->d_ent_cval, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
-    RMB_CUDA(cudaMemset(op->d_ent_ccol, 0xff, std::max<size_t>(1, (size_t)op->nent) * sizeof(int)));
-    op->ntab = (int)tab_off.size();
-    tab_off.push_back((int)ent_col.size());   // extent of the last table
+    if ((rc = upload<double>(&op->d_ent_cent, nullptr, (size_t)op->nent * 4 + 4))) return rc;
+    RMB_CUDA(cudaMemset(op->d_ent_cent, 0, ((size_t)op->nent * 4 + 4) * sizeof(double)));
+    op->ntab = (int)tab_off.size() - 1;
     if ((rc = upload(&op->d_ent_tab, ent_tab.data(), ent_tab.size()))) return rc;
     if ((rc = upload(&op->d_tab_off, tab_off.data(), tab_off.size()))) return rc;
     if ((rc = upload(&op->d_tab_nd, tab_nd.data(), tab_nd.size()))) return rc;
@@ -463,7 +480,7 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
             op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, ph.ent_begin);
         k_compact_tables<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ent_begin, op->d_ent_val, op->d_ent_col, op->d_ent_tab, op->d_tab_off, op->d_tab_nd,
-            op->d_tab_mask, op->d_ent_cval, op->d_ent_ccol);
+            op->d_tab_mask, op->d_ent_cent);
         RMB_CUDA(cudaGetLastError());
         op->n_launches += 2;
     }
@@ -557,15 +574,13 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         if (op->k_complex)
             k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
                 (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                op->d_ent_ccol, op->d_ent_cval, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
-                op->np_max, op->kt_doubles, op->xbuf_elems, op->mf_elems, ep.scale, ep.scale_stride, ep.pdot,
-                ep.npart);
+                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                ep.scale, ep.scale_stride, ep.pdot, ep.npart);
         else
             k_matvec_tiled<false><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
                 (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                op->d_ent_ccol, op->d_ent_cval, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
-                op->np_max, op->kt_doubles, op->xbuf_elems, op->mf_elems, ep.scale, ep.scale_stride, ep.pdot,
-                ep.npart);
+                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                ep.scale, ep.scale_stride, ep.pdot, ep.npart);
         op->n_launches++;
     }
     // scalar kernel for the bra blocks the tiled kernel does not cover (no fused epilogue: callers

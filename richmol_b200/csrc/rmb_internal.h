@@ -76,8 +76,7 @@ struct rmb_operator {
     rmb::ItemD* d_items = nullptr;
     int* d_ent_col = nullptr;
     rmb::cplx* d_ent_val = nullptr;
-    rmb::cplx* d_ent_cval = nullptr; // compacted (non-zero diagonals first) MF values per row
-    int* d_ent_ccol = nullptr;       // ... and their ket m index
+    double* d_ent_cent = nullptr;    // compacted MF entries {re, im, col, pad} (32 bytes), diagonal-major
     int* d_ent_tab = nullptr;        // entry -> global table index
     int* d_tab_off = nullptr;        // [ntab] first entry of each table (int: nent < 2^31)
     int* d_tab_nd = nullptr;         // [ntab] ELL width

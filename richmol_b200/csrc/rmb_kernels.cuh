@@ -99,8 +99,7 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
 __global__ void k_compact_tables(long long nent, long long ent_begin, const cplx* __restrict__ val,
                                  const int* __restrict__ col, const int* __restrict__ ent_tab,
                                  const int* __restrict__ tab_off, const int* __restrict__ tab_nd,
-                                 const unsigned* __restrict__ tab_mask, cplx* __restrict__ cval,
-                                 int* __restrict__ ccol) {
+                                 const unsigned* __restrict__ tab_mask, double* __restrict__ cent) {
     const long long e = ent_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= ent_begin + nent) return;
     const int t = ent_tab[e];
@@ -114,8 +113,14 @@ __global__ void k_compact_tables(long long nent, long long ent_begin, const cplx
         // rows of the table from its extent (tab_off has ntab + 1 entries)
         const int dm1 = (tab_off[t + 1] - tab_off[t]) / nd;
         const long long dst = (long long)tab_off[t] + (long long)q * dm1 + r;
-        cval[dst] = c >= 0 ? val[e] : make_double2(0.0, 0.0);
-        ccol[dst] = c;
+        // 32-byte entry {re, im, col, pad} (struct MfEntry of the tiled matvec)
+        const cplx v = c >= 0 ? val[e] : make_double2(0.0, 0.0);
+        double4 out;
+        out.x = v.x;
+        out.y = v.y;
+        out.z = __hiloint2double(0, c);
+        out.w = 0.0;
+        reinterpret_cast<double4*>(cent)[dst] = out;
     }
 }
 

@@ -14,80 +14,79 @@
 
 namespace rmb {
 
-constexpr int MV2_THREADS = 256;
+constexpr int MV2_CONSUMERS = 224;               // compute threads: one (state, row) pair each
+constexpr int MV2_THREADS = MV2_CONSUMERS + 32;  // + one producer warp issuing the TMA bulk copies
 constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
 constexpr int MV2_SMAX = 32;      // max states per CTA
+constexpr int MV2_STAGES = 2;     // products in flight
 
 struct Item2D {
     long long bra_off;
     int dk1, dm1;
-    int r0, nrows;       // rows (m1) of the tile, nrows <= MV2_THREADS
+    int r0, nrows;       // rows (m1) of the tile, nrows <= MV2_CONSUMERS
     int c0, nc;          // columns (k1) of the tile, nc <= MV2_NCMAX
     int p_begin, p_end;
-    int nst;             // states per CTA (threads = nst * nrows <= MV2_THREADS)
+    int nst;             // states per CTA (compute threads = nst * nrows <= MV2_CONSUMERS)
     int xr_off;          // offset into the per-(item, product) ket row ranges
-    int kt_total;        // doubles of K^T staged in shared memory for this item
+    int kt_total;        // doubles of K^T staged in shared memory for this item (even)
+    int xbuf_elems;      // elements of one staging buffer: max over products of nst * nr * (dk2 | 1)
+    int pad;
 };
 
 struct XRange { int c_lo, nr; };   // ket rows [c_lo, c_lo + nr) needed by (item, product)
 struct Unit2D { int item, s0; };
 
+// compacted MF entry (written by k_compact_tables): value and ket m index of one surviving diagonal
+struct __align__(32) MfEntry { double re, im; int col; int pad[3]; };
+
 // per-product descriptor staged in shared memory at CTA start
 struct ProdS {
-    long long ket_off;   // + c_lo * dk2 already added
-    long long ent_off;   // first entry of the MF table
+    long long ket_off;   // padded offset of the first staged ket row (c_lo already added)
+    long long ent_off;   // first compacted entry of the MF table
     int dk2, nnz, c_lo, nr, xrs, pad0, pad1, pad2;
 };
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// Stage one product for all states of the CTA:
-//  * ket rows X[c_lo .. c_lo+nr) of every active state with coalesced 16-byte cp.async copies; rows are
-//    padded to an odd number of 16-byte words (bank-conflict-free row-strided reads),
-//  * the surviving MF diagonals of the tile rows (values + shared-memory offsets of their ket rows).
-__device__ __forceinline__ void mv2_stage(double2* xb, double2* mfs, int* xos, const ProdS& pr,
-                                          const Item2D& it, const double2* __restrict__ X,
-                                          const long long* __restrict__ sbase, const double2* __restrict__ cval,
-                                          const int* __restrict__ ccol) {
-    // the internal vectors store rows of (dim_k | 1) elements, so the ket rows are one contiguous run
-    const int per_state = pr.nr * pr.xrs;
-    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(xb);
-    const unsigned sstride = (unsigned)per_state * 16u;
-    const double2* src0 = X + pr.ket_off;
-    for (int e = threadIdx.x; e < per_state; e += MV2_THREADS) {
-        const double2* src = src0 + e;
-#pragma unroll 4
-        for (int s = 0; s < it.nst; ++s) {
-            const long long sb = sbase[s];
-            if (sb >= 0)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + s * sstride + e * 16u), "l"(src + sb));
-        }
-    }
-    // MF diagonals: mfs[q][rl], xos[q][rl]
-    const int n = pr.nnz * it.nrows;
-    for (int idx = threadIdx.x; idx < n; idx += MV2_THREADS) {
-        const int q = idx / it.nrows, r = idx - q * it.nrows;
-        const long long e = pr.ent_off + (long long)q * it.dm1 + it.r0 + r;
-        const int col = ccol[e];
-        mfs[q * it.nrows + r] = cval[e];
-        xos[q * it.nrows + r] = col >= 0 ? (col - pr.c_lo) * pr.xrs : 0;   // value is 0 off the block edge
-    }
+// ---- mbarrier / TMA (cp.async.bulk) helpers -----------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA), completion signalled on an mbarrier with the byte count
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // one block product for one thread: acc[k1] += sum_k2 K[k1,k2] * (sum_q MF[q] * X[row_q, k2])
 template <int NC, int NNZ, bool KC>
-__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const double2* __restrict__ mfs,
-                                          const int* __restrict__ xos, int nrows,
-                                          const double* __restrict__ ktp, int dk2, double2 (&acc)[NC]) {
+__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const MfEntry* __restrict__ mfe,
+                                          int nrows, int c_lo, int xrs, const double* __restrict__ ktp, int dk2,
+                                          double2 (&acc)[NC]) {
     double2 mf[NNZ];
     int xo[NNZ];
 #pragma unroll
     for (int q = 0; q < NNZ; ++q) {
-        mf[q] = mfs[q * nrows];
-        xo[q] = xos[q * nrows];
+        const MfEntry e = mfe[q * nrows];
+        mf[q] = make_double2(e.re, e.im);
+        xo[q] = e.col >= 0 ? (e.col - c_lo) * xrs : 0;      // value is 0 when the diagonal leaves the block
     }
 #pragma unroll 2
     for (int k2 = 0; k2 < dk2; ++k2) {
@@ -129,33 +128,44 @@ __device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const 
 }
 
 struct Mv2Smem {
-    double2* xbuf[2];
-    double2* mfs[2];
-    int* xos[2];
+    double2* xbuf[MV2_STAGES];
+    MfEntry* mfe[MV2_STAGES];
     double* kt;
     ProdS* sp;
     long long* sbase;
+    unsigned long long* full;    // [MV2_STAGES] data of a product has landed (TMA transaction bytes)
+    unsigned long long* empty;   // [MV2_STAGES] every consumer warp is done with the stage
 };
 
-// NC = number of register columns (>= it.nc; 1 or even), surplus columns are zero-padded in K^T
+// K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, state tile).
+//
+//  * 8 consumer warps: one thread per (state, row m1) holding all (<= 12) columns k1 of the tile in
+//    registers; per block product p it forms z = sum_q MF_p[m1, q] * X[row_q, k2] on the fly (only the
+//    diagonals that survived the field contraction) and accumulates acc[k1] += K_p[k1, k2] * z with
+//    K_p^T broadcast from shared memory.  H(t) itself is never materialised.
+//  * 1 producer warp: stages, per product and two products ahead of use, the ket rows of every state of
+//    the tile and the MF diagonals with TMA bulk copies (cp.async.bulk) completing on an mbarrier; the
+//    internal vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous,
+//    bank-conflict-free run.
 template <int NC, bool KC>
 __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restrict__ prods,
-                                         const XRange* __restrict__ xrs_tab, const int* __restrict__ ccol,
-                                         const double2* __restrict__ cval, const unsigned* __restrict__ tab_mask,
+                                         const XRange* __restrict__ xrs_tab, const MfEntry* __restrict__ cent,
+                                         const unsigned* __restrict__ tab_mask,
                                          const double* __restrict__ kpool, const double2* __restrict__ X,
                                          double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
                                          int s0, const int* __restrict__ active, const Mv2Smem& sm,
                                          const double* __restrict__ scale, int scale_stride,
                                          double2* __restrict__ pdot, int npart, int item_index) {
     constexpr int KW = KC ? 2 : 1;                       // doubles per K element
+    const bool producer = threadIdx.x >= MV2_CONSUMERS;
     const int sl = threadIdx.x / it.nrows;
     const int rl = threadIdx.x - sl * it.nrows;
     const int st = s0 + sl;
-    const bool work = sl < it.nst && st < nstates && (active == nullptr || active[st]);
+    const bool work = !producer && sl < it.nst && st < nstates && (active == nullptr || active[st]);
     const int np = it.p_end - it.p_begin;
     if (__syncthreads_or(work) == 0) return;             // every state of the tile has converged
 
-    // ---- product descriptors and state base offsets -> shared memory
+    // ---- product descriptors, state base offsets, barriers -> shared memory
     for (int ip = threadIdx.x; ip < np; ip += MV2_THREADS) {
         const ProdD pr = prods[it.p_begin + ip];
         const XRange xr = xrs_tab[it.xr_off + ip];
@@ -174,9 +184,14 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
         const int s = s0 + threadIdx.x;
         sm.sbase[threadIdx.x] = (s < nstates && (active == nullptr || active[s])) ? (long long)s * ldx : -1;
     }
-    __syncthreads();
-    if (np > 0) mv2_stage(sm.xbuf[0], sm.mfs[0], sm.xos[0], sm.sp[0], it, X, sm.sbase, cval, ccol);
-    cp_async_commit();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MV2_STAGES; ++i) {
+            mbar_init(&sm.full[i], 1);                       // producer lane 0 (arrive.expect_tx) + tx bytes
+            mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     // ---- K^T of every product of the item -> shared memory: kt[p][k2][NC]
     {
         int base = 0;
@@ -196,36 +211,63 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
             base += n * KW;
         }
     }
+    __syncthreads();
+
     double2 acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
 
-    int ktbase = 0;
-    for (int ip = 0; ip < np; ++ip) {
-        const int cur = ip & 1;
-        cp_async_wait<0>();
-        __syncthreads();       // product ip has landed; everyone is done with product ip-1
-        if (ip + 1 < np)
-            mv2_stage(sm.xbuf[cur ^ 1], sm.mfs[cur ^ 1], sm.xos[cur ^ 1], sm.sp[ip + 1], it, X, sm.sbase, cval, ccol);
-        cp_async_commit();
-        const int dk2 = sm.sp[ip].dk2, nnz = sm.sp[ip].nnz;
-        if (work) {
-            const double2* xa = sm.xbuf[cur] + (long long)sl * sm.sp[ip].nr * sm.sp[ip].xrs;
-            const double2* mfs = sm.mfs[cur] + rl;
-            const int* xos = sm.xos[cur] + rl;
-            const double* ktp = sm.kt + ktbase;
-            switch (nnz) {
-                case 0: break;
-                case 1: mv2_inner<NC, 1, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
-                case 2: mv2_inner<NC, 2, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
-                case 3: mv2_inner<NC, 3, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
-                case 4: mv2_inner<NC, 4, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
-                default: mv2_inner<NC, 5, KC>(xa, mfs, xos, it.nrows, ktp, dk2, acc); break;
+    if (producer) {
+        // ================= producer warp: TMA bulk copies, MV2_STAGES products ahead =================
+        const int lane = threadIdx.x - MV2_CONSUMERS;
+        int nact = 0;
+        for (int s = 0; s < it.nst; ++s) nact += sm.sbase[s] >= 0 ? 1 : 0;
+        for (int ip = 0; ip < np; ++ip) {
+            const int stage = ip % MV2_STAGES;
+            if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
+            const ProdS d = sm.sp[ip];
+            const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
+            const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)d.nnz * mbytes);
+            __syncwarp();
+            if (xbytes > 0) {
+                for (int s = lane; s < it.nst; s += 32) {
+                    const long long sb = sm.sbase[s];
+                    if (sb >= 0)
+                        tma_load_1d(sm.xbuf[stage] + (long long)s * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
+                                    &sm.full[stage]);
+                }
             }
+            if (lane < d.nnz)
+                tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
+                            mbytes, &sm.full[stage]);
         }
-        ktbase += dk2 * NC * KW;
+    } else {
+        // ================= consumer warps =================
+        int ktbase = 0;
+        for (int ip = 0; ip < np; ++ip) {
+            const int stage = ip % MV2_STAGES;
+            mbar_wait(&sm.full[stage], (ip / MV2_STAGES) & 1);
+            const int dk2 = sm.sp[ip].dk2, nnz = sm.sp[ip].nnz;
+            if (work) {
+                const int nr = sm.sp[ip].nr, xrs = sm.sp[ip].xrs, c_lo = sm.sp[ip].c_lo;
+                const double2* xa = sm.xbuf[stage] + (long long)sl * nr * xrs;
+                const MfEntry* mfe = sm.mfe[stage] + rl;
+                const double* ktp = sm.kt + ktbase;
+                switch (nnz) {
+                    case 0: break;
+                    case 1: mv2_inner<NC, 1, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                    case 2: mv2_inner<NC, 2, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                    case 3: mv2_inner<NC, 3, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                    case 4: mv2_inner<NC, 4, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                    default: mv2_inner<NC, 5, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                }
+            }
+            ktbase += dk2 * NC * KW;
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
+        }
     }
-    cp_async_wait<0>();
     // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
     //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
     double pre = 0.0, pim = 0.0;
@@ -254,10 +296,12 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
         }
     }
     if (pdot != nullptr) {
-        __syncthreads();                        // shared buffers are free again
+        __syncthreads();                        // all stages consumed: the staging buffers are free
         double* red = reinterpret_cast<double*>(sm.xbuf[0]);
-        red[threadIdx.x] = pre;
-        red[MV2_THREADS + threadIdx.x] = pim;
+        if (!producer) {
+            red[threadIdx.x] = pre;
+            red[MV2_CONSUMERS + threadIdx.x] = pim;
+        }
         __syncthreads();
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int s = warp; s < it.nst; s += MV2_THREADS / 32) {
@@ -266,7 +310,7 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
             double a = 0.0, b = 0.0;
             for (int r = lane; r < it.nrows; r += 32) {
                 a += red[s * it.nrows + r];
-                b += red[MV2_THREADS + s * it.nrows + r];
+                b += red[MV2_CONSUMERS + s * it.nrows + r];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -282,28 +326,26 @@ template <bool KC>
 __global__ void __launch_bounds__(MV2_THREADS, 2)
 k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ items,
                const ProdD* __restrict__ prods, const XRange* __restrict__ xrs_tab,
-               const int* __restrict__ ccol, const double2* __restrict__ cval,
-               const unsigned* __restrict__ tab_mask, const double* __restrict__ kpool,
-               const double2* __restrict__ X, double2* __restrict__ Y, long long ldx, long long ldy,
-               int nstates, const int* __restrict__ active, int np_max, int kt_doubles, int xbuf_elems,
-               int mf_elems, const double* __restrict__ scale, int scale_stride, double2* __restrict__ pdot,
-               int npart) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Mv2Smem sm;
-    sm.xbuf[0] = reinterpret_cast<double2*>(smem_raw);
-    sm.xbuf[1] = sm.xbuf[0] + xbuf_elems;
-    sm.mfs[0] = sm.xbuf[1] + xbuf_elems;
-    sm.mfs[1] = sm.mfs[0] + mf_elems;
-    sm.kt = reinterpret_cast<double*>(sm.mfs[1] + mf_elems);
-    sm.sp = reinterpret_cast<ProdS*>(sm.kt + kt_doubles);
-    sm.sbase = reinterpret_cast<long long*>(sm.sp + np_max);
-    sm.xos[0] = reinterpret_cast<int*>(sm.sbase + MV2_SMAX);
-    sm.xos[1] = sm.xos[0] + mf_elems;
+               const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
+               const double* __restrict__ kpool, const double2* __restrict__ X, double2* __restrict__ Y,
+               long long ldx, long long ldy, int nstates, const int* __restrict__ active,
+               const double* __restrict__ scale, int scale_stride, double2* __restrict__ pdot, int npart) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const Unit2D u = units[blockIdx.x];
     const Item2D it = items[u.item];
+    // shared memory is carved with the sizes of this item (the launch reserves the maximum over items)
+    Mv2Smem sm;
+    unsigned char* p = smem_raw;
+    for (int i = 0; i < MV2_STAGES; ++i) { sm.xbuf[i] = reinterpret_cast<double2*>(p); p += (size_t)it.xbuf_elems * 16; }
+    for (int i = 0; i < MV2_STAGES; ++i) { sm.mfe[i] = reinterpret_cast<MfEntry*>(p); p += (size_t)MV2_NDMAX * it.nrows * sizeof(MfEntry); }
+    sm.kt = reinterpret_cast<double*>(p); p += (size_t)it.kt_total * 8;
+    sm.sp = reinterpret_cast<ProdS*>(p); p += (size_t)(it.p_end - it.p_begin) * sizeof(ProdS);
+    sm.sbase = reinterpret_cast<long long*>(p); p += MV2_SMAX * 8;
+    sm.full = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
+    sm.empty = reinterpret_cast<unsigned long long*>(p);
 #define RMB_CASE(N)                                                                                        \
     case N:                                                                                                \
-        mv2_body<N, KC>(it, prods, xrs_tab, ccol, cval, tab_mask, kpool, X, Y, ldx, ldy, nstates,          \
+        mv2_body<N, KC>(it, prods, xrs_tab, cent, tab_mask, kpool, X, Y, ldx, ldy, nstates,                \
                         u.s0, active, sm, scale, scale_stride, pdot, npart, u.item);                       \
         break;
     switch (it.nc == 1 ? 1 : (it.nc + 1) & ~1) {
