@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <map>
 #include <numeric>
 
 #include "rmb_kernels.cuh"
@@ -58,7 +59,8 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_items);
     cudaFree(op->d_pmap);
     cudaFree(op->d_items2);
-    cudaFree(op->d_xranges);
+    cudaFree(op->d_gdesc);
+    cudaFree(op->d_ktpool);
     cudaFree(op->d_units);
     cudaFree(op->d_ent_col);
     cudaFree(op->d_ent_val);
@@ -262,12 +264,15 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     }
     auto item_smem = [](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod) {
         return (size_t)MV2_STAGES * xbuf_elems * 16 + (size_t)MV2_STAGES * MV2_NDMAX * nrows * sizeof(MfEntry) +
-               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + MV2_SMAX * 8 + 2 * MV2_STAGES * 8 + 128;
+               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (2 * MV2_STAGES + 1) * 8 + (size_t)nprod * 4 + 128;
     };
     const char* force = getenv("RMB_MATVEC");
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
     std::vector<XRange> xranges;
+    std::vector<ProdS> gdesc;                 // static per-(item, product) descriptors, shared-memory layout
+    std::vector<double> ktpool;               // K^T images per (bra block, column chunk), shared-memory layout
+    std::map<std::pair<int, int>, long long> kt_index;
     const size_t smem_budget = 108 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
     for (int b = 0; b < d->nblocks; ++b) {
         const int dk1 = d->blk_dk[b], dm1 = d->blk_dm[b];
@@ -283,7 +288,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         }
         // ---- tiled kernel: row tiles (<= 128 rows, one thread per row and state pair) x column
         //      chunks (<= 16); falls back to the scalar kernel when the tile does not fit
-        bool fast = !force_scalar && ndmax <= MV2_NDMAX;   // diagonal slots handled in registers
+        bool fast = !force_scalar && ndmax <= MV2_NDMAX &&   // diagonal slots handled in registers
+                    bra_begin[b + 1] - bra_begin[b] <= 128;
         if (fast) {
             int best_nt = 0, best_nst = 0;
             double best_util = -1;
@@ -327,12 +333,14 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         it.p_end = bra_begin[b + 1];
                         it.nst = best_nst;
                         it.xr_off = (int)xranges.size();
+                        it.desc_off = (int)gdesc.size();
                         const int ncp = it.nc == 1 ? 1 : ((it.nc + 1) & ~1);
+                        const int kw = kc ? 2 : 1;
                         int ktd = 0;
                         int xbe = 256;
                         for (int p = it.p_begin; p < it.p_end; ++p) {
                             const ProdD& q = op->h_prods[p];
-                            ktd += q.dk2 * ncp * (kc ? 2 : 1);
+                            ktd += q.dk2 * ncp * kw;
                             int lo = q.dm2, hi = -1;
                             for (int r = it.r0; r < it.r0 + it.nrows; ++r)
                                 for (int j = 0; j < q.nd; ++j) {
@@ -344,10 +352,38 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             xr.nr = hi < 0 ? 0 : hi - lo + 1;
                             xranges.push_back(xr);
                             xbe = std::max(xbe, it.nst * xr.nr * (q.dk2 | 1));
+                            ProdS ds;
+                            ds.ket_off = q.ket_off + (long long)xr.c_lo * (q.dk2 | 1);
+                            ds.ent_off = q.ent_off;
+                            ds.dk2 = q.dk2;
+                            ds.nnz = 0;
+                            ds.c_lo = xr.c_lo;
+                            ds.nr = xr.nr;
+                            ds.xrs = q.dk2 | 1;
+                            ds.tab = q.tab;
+                            ds.pad1 = ds.pad2 = 0;
+                            gdesc.push_back(ds);
                         }
                         it.kt_total = (ktd + 1) & ~1;
+                        // K^T image [product][k2][ncp] of this (bra block, column chunk), built once
+                        auto key = std::make_pair(b, c0);
+                        auto found = kt_index.find(key);
+                        if (found == kt_index.end()) {
+                            const long long off = (long long)ktpool.size();
+                            kt_index[key] = off;
+                            for (int p = it.p_begin; p < it.p_end; ++p) {
+                                const ProdD& q = op->h_prods[p];
+                                for (int k2 = 0; k2 < q.dk2; ++k2)
+                                    for (int c = 0; c < ncp; ++c)
+                                        for (int w = 0; w < kw; ++w)
+                                            ktpool.push_back(c < it.nc ? kpool[(size_t)(q.koff + (long long)(c0 + c) * q.dk2 + k2) * kw + w] : 0.0);
+                            }
+                            while (ktpool.size() % 2) ktpool.push_back(0.0);   // 16-byte aligned images
+                            it.kt_off = off;
+                        } else {
+                            it.kt_off = found->second;
+                        }
                         it.xbuf_elems = xbe;
-                        it.pad = 0;
                         op->matvec2_smem = std::max(op->matvec2_smem,
                                                     item_smem((size_t)xbe, it.nrows, (size_t)it.kt_total, it.p_end - it.p_begin));
                         items2.push_back(it);
@@ -416,7 +452,10 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     if ((rc = upload(&op->d_prods, op->h_prods.data(), op->h_prods.size()))) return rc;
     if ((rc = upload(&op->d_items, op->h_items.data(), op->h_items.size()))) return rc;
     if ((rc = upload((Item2D**)&op->d_items2, items2.data(), items2.size()))) return rc;
-    if ((rc = upload((XRange**)&op->d_xranges, xranges.data(), xranges.size()))) return rc;
+    if ((rc = upload((ProdS**)&op->d_gdesc, gdesc.data(), gdesc.size()))) return rc;
+    ktpool.push_back(0.0);
+    ktpool.push_back(0.0);
+    if ((rc = upload(&op->d_ktpool, ktpool.data(), ktpool.size()))) return rc;
     // the opt-in limit is a per-function, process-wide attribute: only ever raise it
     static size_t g_tiled_smem = 48 * 1024;
     if (op->matvec2_smem > g_tiled_smem) {
@@ -573,13 +612,13 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         }
         if (op->k_complex)
             k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
-                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, (const ProdS*)op->d_gdesc,
+                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_ktpool, X, Y, ldx, ldy, (int)nstates, active,
                 ep.scale, ep.scale_stride, ep.pdot, ep.npart);
         else
             k_matvec_tiled<false><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
-                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, op->d_prods, (const XRange*)op->d_xranges,
-                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_kpool, X, Y, ldx, ldy, (int)nstates, active,
+                (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, (const ProdS*)op->d_gdesc,
+                (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_ktpool, X, Y, ldx, ldy, (int)nstates, active,
                 ep.scale, ep.scale_stride, ep.pdot, ep.npart);
         op->n_launches++;
     }

@@ -35,6 +35,7 @@ struct ItemD {
 // tiled matvec (rmb_matvec.cuh)
 struct Item2D;
 struct XRange;
+struct ProdS;
 struct Unit2D;
 
 struct PartH {
@@ -92,7 +93,8 @@ struct rmb_operator {
     // tiled matvec
     int nitems2 = 0;
     void* d_items2 = nullptr;        // Item2D[]
-    void* d_xranges = nullptr;       // XRange[]
+    void* d_gdesc = nullptr;         // ProdS[]: static per-(item, product) descriptors
+    double* d_ktpool = nullptr;      // K^T images in shared-memory layout
     void* d_units = nullptr;         // Unit2D[] for `units_nstates` states
     long long units_nstates = -1;
     int nunits = 0;

@@ -31,7 +31,8 @@ struct Item2D {
     int xr_off;          // offset into the per-(item, product) ket row ranges
     int kt_total;        // doubles of K^T staged in shared memory for this item (even)
     int xbuf_elems;      // elements of one staging buffer: max over products of nst * nr * (dk2 | 1)
-    int pad;
+    int desc_off;        // first static descriptor (ProdS) of the item in the global descriptor table
+    long long kt_off;    // offset (doubles) of the item's K^T image in the global K^T pool
 };
 
 struct XRange { int c_lo, nr; };   // ket rows [c_lo, c_lo + nr) needed by (item, product)
@@ -41,10 +42,11 @@ struct Unit2D { int item, s0; };
 struct __align__(32) MfEntry { double re, im; int col; int pad[3]; };
 
 // per-product descriptor staged in shared memory at CTA start
+// (built on the host; `nnz` is filled in by the producer warp from the field-dependent diagonal masks)
 struct ProdS {
     long long ket_off;   // padded offset of the first staged ket row (c_lo already added)
     long long ent_off;   // first compacted entry of the MF table
-    int dk2, nnz, c_lo, nr, xrs, pad0, pad1, pad2;
+    int dk2, nnz, c_lo, nr, xrs, tab, pad1, pad2;
 };
 
 // ---- mbarrier / TMA (cp.async.bulk) helpers -----------------------------------------------------
@@ -132,9 +134,9 @@ struct Mv2Smem {
     MfEntry* mfe[MV2_STAGES];
     double* kt;
     ProdS* sp;
-    long long* sbase;
     unsigned long long* full;    // [MV2_STAGES] data of a product has landed (TMA transaction bytes)
     unsigned long long* empty;   // [MV2_STAGES] every consumer warp is done with the stage
+    unsigned long long* setup;   // K^T image + descriptors have landed, nnz filled in
 };
 
 // K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, state tile).
@@ -148,10 +150,9 @@ struct Mv2Smem {
 //    internal vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous,
 //    bank-conflict-free run.
 template <int NC, bool KC>
-__device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restrict__ prods,
-                                         const XRange* __restrict__ xrs_tab, const MfEntry* __restrict__ cent,
-                                         const unsigned* __restrict__ tab_mask,
-                                         const double* __restrict__ kpool, const double2* __restrict__ X,
+__device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restrict__ gdesc,
+                                         const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
+                                         const double* __restrict__ ktpool, const double2* __restrict__ X,
                                          double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
                                          int s0, const int* __restrict__ active, const Mv2Smem& sm,
                                          const double* __restrict__ scale, int scale_stride,
@@ -165,51 +166,14 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
     const int np = it.p_end - it.p_begin;
     if (__syncthreads_or(work) == 0) return;             // every state of the tile has converged
 
-    // ---- product descriptors, state base offsets, barriers -> shared memory
-    for (int ip = threadIdx.x; ip < np; ip += MV2_THREADS) {
-        const ProdD pr = prods[it.p_begin + ip];
-        const XRange xr = xrs_tab[it.xr_off + ip];
-        ProdS d;
-        d.ket_off = pr.ket_off + (long long)xr.c_lo * (pr.dk2 | 1);
-        d.ent_off = pr.ent_off;
-        d.dk2 = pr.dk2;
-        d.nnz = min(__popc(tab_mask[pr.tab]), MV2_NDMAX);   // diagonals that survived the field contraction
-        d.c_lo = xr.c_lo;
-        d.nr = xr.nr;
-        d.xrs = pr.dk2 | 1;
-        d.pad0 = d.pad1 = d.pad2 = 0;
-        sm.sp[ip] = d;
-    }
-    if (threadIdx.x < it.nst) {
-        const int s = s0 + threadIdx.x;
-        sm.sbase[threadIdx.x] = (s < nstates && (active == nullptr || active[s])) ? (long long)s * ldx : -1;
-    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < MV2_STAGES; ++i) {
             mbar_init(&sm.full[i], 1);                       // producer lane 0 (arrive.expect_tx) + tx bytes
             mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
         }
+        mbar_init(sm.setup, 1 + 32);                         // expect_tx arrival + every producer lane
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    // ---- K^T of every product of the item -> shared memory: kt[p][k2][NC]
-    {
-        int base = 0;
-        for (int ip = 0; ip < np; ++ip) {
-            const ProdD pr = prods[it.p_begin + ip];
-            const int n = pr.dk2 * NC;
-            for (int idx = threadIdx.x; idx < n; idx += MV2_THREADS) {
-                const int k2 = idx / NC, c = idx - k2 * NC;
-                if (KC) {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (c < it.nc) v = reinterpret_cast<const double2*>(kpool)[pr.koff + (long long)(it.c0 + c) * pr.dk2 + k2];
-                    reinterpret_cast<double2*>(sm.kt + base)[idx] = v;
-                } else {
-                    sm.kt[base + idx] = (c < it.nc) ? kpool[pr.koff + (long long)(it.c0 + c) * pr.dk2 + k2] : 0.0;
-                }
-            }
-            base += n * KW;
-        }
     }
     __syncthreads();
 
@@ -220,35 +184,63 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
     if (producer) {
         // ================= producer warp: TMA bulk copies, MV2_STAGES products ahead =================
         const int lane = threadIdx.x - MV2_CONSUMERS;
-        int nact = 0;
-        for (int s = 0; s < it.nst; ++s) nact += sm.sbase[s] >= 0 ? 1 : 0;
+        // the K^T image of all products and the static descriptors were laid out on the host exactly as
+        // they sit in shared memory: two bulk copies
+        if (lane == 0) {
+            const unsigned kbytes = (unsigned)it.kt_total * 8u, dbytes = (unsigned)np * (unsigned)sizeof(ProdS);
+            mbar_arrive_expect_tx(sm.setup, kbytes + dbytes);
+            if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
+            if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
+        }
+        // state offsets of this tile (one lane per state)
+        long long sb = -1;
+        if (lane < it.nst) {
+            const int s = s0 + lane;
+            if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
+        }
+        const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
+        // diagonals that survived the field contraction (field-dependent: read from the masks)
+        int my_nnz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ip = lane + 32 * j;
+            my_nnz[j] = ip < np ? min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX) : 0;
+        }
+        // nnz goes to its own shared array (the descriptors are still in flight); the setup barrier
+        // completes when the bulk copies have landed and every producer lane has published its values
+        int* snnz = reinterpret_cast<int*>(sm.setup + 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ip = lane + 32 * j;
+            if (ip < np) snnz[ip] = my_nnz[j];
+        }
+        mbar_arrive(sm.setup);                               // release: snnz visible to whoever waits
+        mbar_wait(sm.setup, 0);
         for (int ip = 0; ip < np; ++ip) {
             const int stage = ip % MV2_STAGES;
             if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
             const ProdS d = sm.sp[ip];
+            const int nnz = snnz[ip];
             const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
             const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)d.nnz * mbytes);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
             __syncwarp();
-            if (xbytes > 0) {
-                for (int s = lane; s < it.nst; s += 32) {
-                    const long long sb = sm.sbase[s];
-                    if (sb >= 0)
-                        tma_load_1d(sm.xbuf[stage] + (long long)s * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
-                                    &sm.full[stage]);
-                }
-            }
-            if (lane < d.nnz)
+            if (xbytes > 0 && sb >= 0)
+                tma_load_1d(sm.xbuf[stage] + (long long)lane * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
+                            &sm.full[stage]);
+            if (lane < nnz)
                 tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
                             mbytes, &sm.full[stage]);
         }
     } else {
         // ================= consumer warps =================
+        const int* snnz = reinterpret_cast<const int*>(sm.setup + 1);
+        mbar_wait(sm.setup, 0);
         int ktbase = 0;
         for (int ip = 0; ip < np; ++ip) {
             const int stage = ip % MV2_STAGES;
             mbar_wait(&sm.full[stage], (ip / MV2_STAGES) & 1);
-            const int dk2 = sm.sp[ip].dk2, nnz = sm.sp[ip].nnz;
+            const int dk2 = sm.sp[ip].dk2, nnz = snnz[ip];
             if (work) {
                 const int nr = sm.sp[ip].nr, xrs = sm.sp[ip].xrs, c_lo = sm.sp[ip].c_lo;
                 const double2* xa = sm.xbuf[stage] + (long long)sl * nr * xrs;
@@ -325,27 +317,28 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdD* __restri
 template <bool KC>
 __global__ void __launch_bounds__(MV2_THREADS, 2)
 k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ items,
-               const ProdD* __restrict__ prods, const XRange* __restrict__ xrs_tab,
-               const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
-               const double* __restrict__ kpool, const double2* __restrict__ X, double2* __restrict__ Y,
-               long long ldx, long long ldy, int nstates, const int* __restrict__ active,
-               const double* __restrict__ scale, int scale_stride, double2* __restrict__ pdot, int npart) {
+               const ProdS* __restrict__ gdesc, const MfEntry* __restrict__ cent,
+               const unsigned* __restrict__ tab_mask, const double* __restrict__ ktpool,
+               const double2* __restrict__ X, double2* __restrict__ Y, long long ldx, long long ldy,
+               int nstates, const int* __restrict__ active, const double* __restrict__ scale,
+               int scale_stride, double2* __restrict__ pdot, int npart) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Unit2D u = units[blockIdx.x];
     const Item2D it = items[u.item];
+    const int np = it.p_end - it.p_begin;
     // shared memory is carved with the sizes of this item (the launch reserves the maximum over items)
     Mv2Smem sm;
     unsigned char* p = smem_raw;
     for (int i = 0; i < MV2_STAGES; ++i) { sm.xbuf[i] = reinterpret_cast<double2*>(p); p += (size_t)it.xbuf_elems * 16; }
     for (int i = 0; i < MV2_STAGES; ++i) { sm.mfe[i] = reinterpret_cast<MfEntry*>(p); p += (size_t)MV2_NDMAX * it.nrows * sizeof(MfEntry); }
     sm.kt = reinterpret_cast<double*>(p); p += (size_t)it.kt_total * 8;
-    sm.sp = reinterpret_cast<ProdS*>(p); p += (size_t)(it.p_end - it.p_begin) * sizeof(ProdS);
-    sm.sbase = reinterpret_cast<long long*>(p); p += MV2_SMAX * 8;
+    sm.sp = reinterpret_cast<ProdS*>(p); p += (size_t)np * sizeof(ProdS);
     sm.full = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
-    sm.empty = reinterpret_cast<unsigned long long*>(p);
+    sm.empty = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
+    sm.setup = reinterpret_cast<unsigned long long*>(p);     // followed by int snnz[np]
 #define RMB_CASE(N)                                                                                        \
     case N:                                                                                                \
-        mv2_body<N, KC>(it, prods, xrs_tab, cent, tab_mask, kpool, X, Y, ldx, ldy, nstates,                \
+        mv2_body<N, KC>(it, gdesc, cent, tab_mask, ktpool, X, Y, ldx, ldy, nstates,                        \
                         u.s0, active, sm, scale, scale_stride, pdot, npart, u.item);                       \
         break;
     switch (it.nc == 1 ? 1 : (it.nc + 1) & ~1) {
