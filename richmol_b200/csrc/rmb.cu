@@ -296,7 +296,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             const int nt0 = (dm1 + MV2_CONSUMERS - 1) / MV2_CONSUMERS;
             for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
                 const int nr = (dm1 + nt - 1) / nt;
-                int nst = std::min(MV2_SMAX, MV2_CONSUMERS / nr);
+                int nst = 2 * std::min(MV2_SMAX / 2, MV2_CONSUMERS / nr);   // two states per thread
                 // shared memory of the item (exactly what the kernel carves): staging buffers for the ket
                 // rows and MF diagonals, K^T of all products, descriptors, state offsets, barriers
                 auto need = [&](int nst_) {
@@ -311,9 +311,9 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                     kt = (kt + 1) & ~(size_t)1;
                     return item_smem(xb, nr, kt, bra_begin[b + 1] - bra_begin[b]);
                 };
-                while (nst > 1 && need(nst) > smem_budget) --nst;
+                while (nst > 2 && need(nst) > smem_budget) nst -= 2;
                 if (need(nst) > smem_budget) continue;
-                const double util = (double)nr * nst / MV2_CONSUMERS * ((double)dm1 / (nr * nt));
+                const double util = (double)nr * (nst / 2) / MV2_CONSUMERS * ((double)dm1 / (nr * nt));
                 if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_nst = nst; }
             }
             if (best_nt == 0) fast = false;

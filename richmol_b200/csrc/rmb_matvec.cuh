@@ -14,7 +14,7 @@
 
 namespace rmb {
 
-constexpr int MV2_CONSUMERS = 224;               // compute threads: one (state, row) pair each
+constexpr int MV2_CONSUMERS = 128;               // compute threads: one row of TWO states each
 constexpr int MV2_THREADS = MV2_CONSUMERS + 32;  // + one producer warp issuing the TMA bulk copies
 constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
@@ -27,7 +27,7 @@ struct Item2D {
     int r0, nrows;       // rows (m1) of the tile, nrows <= MV2_CONSUMERS
     int c0, nc;          // columns (k1) of the tile, nc <= MV2_NCMAX
     int p_begin, p_end;
-    int nst;             // states per CTA (compute threads = nst * nrows <= MV2_CONSUMERS)
+    int nst;             // states per CTA, even (compute threads = nst/2 * nrows <= MV2_CONSUMERS)
     int xr_off;          // offset into the per-(item, product) ket row ranges
     int kt_total;        // doubles of K^T staged in shared memory for this item (even)
     int xbuf_elems;      // elements of one staging buffer: max over products of nst * nr * (dk2 | 1)
@@ -77,11 +77,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// one block product for one thread: acc[k1] += sum_k2 K[k1,k2] * (sum_q MF[q] * X[row_q, k2])
+// one block product for one thread (one row m1 of two states A, B):
+//   acc[k1] += sum_k2 K[k1,k2] * (sum_q MF[q] * X[row_q, k2])
+// K^T values are loaded once per k2 and used for both states (halves the shared-memory traffic per DFMA)
 template <int NC, int NNZ, bool KC>
-__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const MfEntry* __restrict__ mfe,
-                                          int nrows, int c_lo, int xrs, const double* __restrict__ ktp, int dk2,
-                                          double2 (&acc)[NC]) {
+__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const double2* __restrict__ xb,
+                                          const MfEntry* __restrict__ mfe, int nrows, int c_lo, int xrs,
+                                          const double* __restrict__ ktp, int dk2, double2 (&accA)[NC],
+                                          double2 (&accB)[NC]) {
     double2 mf[NNZ];
     int xo[NNZ];
 #pragma unroll
@@ -92,38 +95,52 @@ __device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const 
     }
 #pragma unroll 2
     for (int k2 = 0; k2 < dk2; ++k2) {
-        double2 z = make_double2(0.0, 0.0);
+        double2 zA = make_double2(0.0, 0.0), zB = make_double2(0.0, 0.0);
 #pragma unroll
         for (int q = 0; q < NNZ; ++q) {
-            const double2 a = xa[xo[q] + k2];
-            z.x = fma(mf[q].x, a.x, z.x);
-            z.y = fma(mf[q].x, a.y, z.y);
-            z.x = fma(-mf[q].y, a.y, z.x);
-            z.y = fma(mf[q].y, a.x, z.y);
+            const double2 a = xa[xo[q] + k2], b = xb[xo[q] + k2];
+            zA.x = fma(mf[q].x, a.x, zA.x);
+            zA.y = fma(mf[q].x, a.y, zA.y);
+            zB.x = fma(mf[q].x, b.x, zB.x);
+            zB.y = fma(mf[q].x, b.y, zB.y);
+            zA.x = fma(-mf[q].y, a.y, zA.x);
+            zA.y = fma(mf[q].y, a.x, zA.y);
+            zB.x = fma(-mf[q].y, b.y, zB.x);
+            zB.y = fma(mf[q].y, b.x, zB.y);
         }
         if (KC) {
             const double2* krow = reinterpret_cast<const double2*>(ktp) + k2 * NC;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const double2 kv = krow[c];
-                acc[c].x = fma(kv.x, z.x, acc[c].x);
-                acc[c].y = fma(kv.x, z.y, acc[c].y);
-                acc[c].x = fma(-kv.y, z.y, acc[c].x);
-                acc[c].y = fma(kv.y, z.x, acc[c].y);
+                accA[c].x = fma(kv.x, zA.x, accA[c].x);
+                accA[c].y = fma(kv.x, zA.y, accA[c].y);
+                accB[c].x = fma(kv.x, zB.x, accB[c].x);
+                accB[c].y = fma(kv.x, zB.y, accB[c].y);
+                accA[c].x = fma(-kv.y, zA.y, accA[c].x);
+                accA[c].y = fma(kv.y, zA.x, accA[c].y);
+                accB[c].x = fma(-kv.y, zB.y, accB[c].x);
+                accB[c].y = fma(kv.y, zB.x, accB[c].y);
             }
         } else if (NC == 1) {
             const double kv = ktp[k2];
-            acc[0].x = fma(kv, z.x, acc[0].x);
-            acc[0].y = fma(kv, z.y, acc[0].y);
+            accA[0].x = fma(kv, zA.x, accA[0].x);
+            accA[0].y = fma(kv, zA.y, accA[0].y);
+            accB[0].x = fma(kv, zB.x, accB[0].x);
+            accB[0].y = fma(kv, zB.y, accB[0].y);
         } else {
             const double2* krow = reinterpret_cast<const double2*>(ktp + k2 * NC);
 #pragma unroll
             for (int c2 = 0; c2 < NC / 2; ++c2) {
                 const double2 kv = krow[c2];
-                acc[2 * c2].x = fma(kv.x, z.x, acc[2 * c2].x);
-                acc[2 * c2].y = fma(kv.x, z.y, acc[2 * c2].y);
-                acc[2 * c2 + 1].x = fma(kv.y, z.x, acc[2 * c2 + 1].x);
-                acc[2 * c2 + 1].y = fma(kv.y, z.y, acc[2 * c2 + 1].y);
+                accA[2 * c2].x = fma(kv.x, zA.x, accA[2 * c2].x);
+                accA[2 * c2].y = fma(kv.x, zA.y, accA[2 * c2].y);
+                accB[2 * c2].x = fma(kv.x, zB.x, accB[2 * c2].x);
+                accB[2 * c2].y = fma(kv.x, zB.y, accB[2 * c2].y);
+                accA[2 * c2 + 1].x = fma(kv.y, zA.x, accA[2 * c2 + 1].x);
+                accA[2 * c2 + 1].y = fma(kv.y, zA.y, accA[2 * c2 + 1].y);
+                accB[2 * c2 + 1].x = fma(kv.y, zB.x, accB[2 * c2 + 1].x);
+                accB[2 * c2 + 1].y = fma(kv.y, zB.y, accB[2 * c2 + 1].y);
             }
         }
     }
@@ -159,10 +176,13 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
                                          double2* __restrict__ pdot, int npart, int item_index) {
     constexpr int KW = KC ? 2 : 1;                       // doubles per K element
     const bool producer = threadIdx.x >= MV2_CONSUMERS;
-    const int sl = threadIdx.x / it.nrows;
+    const int sl = threadIdx.x / it.nrows;               // state pair of this thread
     const int rl = threadIdx.x - sl * it.nrows;
-    const int st = s0 + sl;
-    const bool work = !producer && sl < it.nst && st < nstates && (active == nullptr || active[st]);
+    const int stA = s0 + 2 * sl, stB = stA + 1;
+    const bool inb = !producer && 2 * sl < it.nst;
+    const bool vA = inb && stA < nstates && (active == nullptr || active[stA]);
+    const bool vB = inb && stB < nstates && (active == nullptr || active[stB]);
+    const bool work = vA || vB;
     const int np = it.p_end - it.p_begin;
     if (__syncthreads_or(work) == 0) return;             // every state of the tile has converged
 
@@ -177,9 +197,9 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
     }
     __syncthreads();
 
-    double2 acc[NC];
+    double2 accA[NC], accB[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
+    for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
 
     if (producer) {
         // ================= producer warp: TMA bulk copies, MV2_STAGES products ahead =================
@@ -243,16 +263,17 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
             const int dk2 = sm.sp[ip].dk2, nnz = snnz[ip];
             if (work) {
                 const int nr = sm.sp[ip].nr, xrs = sm.sp[ip].xrs, c_lo = sm.sp[ip].c_lo;
-                const double2* xa = sm.xbuf[stage] + (long long)sl * nr * xrs;
+                const double2* xa = sm.xbuf[stage] + (long long)(2 * sl) * nr * xrs;
+                const double2* xb = xa + (long long)nr * xrs;   // an inactive partner reads stale data: never stored
                 const MfEntry* mfe = sm.mfe[stage] + rl;
                 const double* ktp = sm.kt + ktbase;
                 switch (nnz) {
                     case 0: break;
-                    case 1: mv2_inner<NC, 1, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
-                    case 2: mv2_inner<NC, 2, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
-                    case 3: mv2_inner<NC, 3, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
-                    case 4: mv2_inner<NC, 4, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
-                    default: mv2_inner<NC, 5, KC>(xa, mfe, it.nrows, c_lo, xrs, ktp, dk2, acc); break;
+                    case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    default: mv2_inner<NC, 5, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
                 }
             }
             ktbase += dk2 * NC * KW;
@@ -262,9 +283,9 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
     }
     // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
     //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
-    double pre = 0.0, pim = 0.0;
-    if (work) {
-        const long long row_off = it.bra_off + (long long)(it.r0 + rl) * (it.dk1 | 1) + it.c0;
+    double preA = 0.0, pimA = 0.0, preB = 0.0, pimB = 0.0;
+    const long long row_off = it.bra_off + (long long)(it.r0 + rl) * (it.dk1 | 1) + it.c0;
+    auto finish = [&](double2 (&acc)[NC], int st, double& pre, double& pim) {
         if (scale != nullptr) {
             const double sc = scale[(long long)st * scale_stride];
 #pragma unroll
@@ -286,13 +307,18 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
                     pim += acc[c].x * v.y - acc[c].y * v.x;
                 }
         }
-    }
+    };
+    if (vA) finish(accA, stA, preA, pimA);
+    if (vB) finish(accB, stB, preB, pimB);
     if (pdot != nullptr) {
         __syncthreads();                        // all stages consumed: the staging buffers are free
-        double* red = reinterpret_cast<double*>(sm.xbuf[0]);
-        if (!producer) {
-            red[threadIdx.x] = pre;
-            red[MV2_CONSUMERS + threadIdx.x] = pim;
+        double* red = reinterpret_cast<double*>(sm.xbuf[0]);   // [2][nst][nrows]
+        const int half = it.nst * it.nrows;
+        if (inb) {
+            red[(2 * sl) * it.nrows + rl] = preA;
+            red[(2 * sl + 1) * it.nrows + rl] = preB;
+            red[half + (2 * sl) * it.nrows + rl] = pimA;
+            red[half + (2 * sl + 1) * it.nrows + rl] = pimB;
         }
         __syncthreads();
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,7 +328,7 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
             double a = 0.0, b = 0.0;
             for (int r = lane; r < it.nrows; r += 32) {
                 a += red[s * it.nrows + r];
-                b += red[MV2_CONSUMERS + s * it.nrows + r];
+                b += red[half + s * it.nrows + r];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
