@@ -329,17 +329,13 @@ class _Endless:
 
 
 def op_info(op):
-    """flops / operator bytes per state-matvec from the packed tables (formulae of SURVEY.md 8d)."""
-    flops, opb = 0.0, 0.0
-    b = op.basis
-    for p in op.parts:
-        kc = 8.0 if p.k_is_complex else 4.0
-        for b1, b2, t in zip(p.pr_bra, p.pr_ket, p.pr_table):
-            dm1, dk1, dk2 = float(b.dm[b1]), float(b.dk[b1]), float(b.dk[b2])
-            flops += kc * dm1 * dk1 * dk2 + 8.0 * float(p.tb_nd[t]) * dm1 * dk2
-            opb += (16.0 if p.k_is_complex else 8.0) * dk1 * dk2
-        opb += 20.0 * p.nent
-    return {"flops_per_state": flops, "op_bytes": opb}
+    """flops / operator bytes per state-matvec for the field currently applied (formulae of SURVEY.md 8d;
+    only the M diagonals that survive the field contraction are counted, as in the reference's CSR)."""
+    import ctypes as C
+    from richmol_b200 import _lib
+    fl, by = C.c_double(), C.c_double()
+    _lib.check(_lib.lib().rmb_operator_work(op.handle, C.byref(fl), C.byref(by), None))
+    return {"flops_per_state": fl.value, "op_bytes": by.value}
 
 
 def measured_peaks():

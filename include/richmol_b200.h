@@ -54,7 +54,8 @@ typedef struct rmb_part_desc {
     int32_t ntables;
     const int32_t* tb_dm1;     /* [ntables] rows (bra m quanta)                                    */
     const int32_t* tb_dm2;     /* [ntables] columns (ket m quanta)                                 */
-    const int32_t* tb_nd;      /* [ntables] ELL width = max entries per row of the union pattern   */
+    const int32_t* tb_nd;      /* [ntables] ELL width = number of distinct diagonals (col - row) of the
+                                  union pattern; slot j of every row is the same diagonal            */
     const int64_t* tb_off;     /* [ntables+1] entry offset; table t has tb_dm1[t]*tb_nd[t] entries,
                                   row-major (m1, j)                                                */
     const int32_t* ent_col;    /* [nent] ket m index of the entry, -1 = padding                    */
@@ -136,6 +137,10 @@ int32_t rmb_set_workspace_budget(rmb_operator* op, int64_t bytes);
 /* counters since handle creation: [0] kernel launches, [1] matvec launches, [2] Lanczos
  * iterations (batch-level), [3] state-matvecs                                                       */
 int32_t rmb_get_counters(const rmb_operator* op, int64_t* out4);
+/* algorithmic work of one state-matvec with the field currently applied: flops =
+ * sum_products [4(8) dm1 dk1 dk2 + 8 nnz_diag dm1 dk2], counting only the M diagonals that survived the
+ * field contraction; op_bytes = K blocks + compacted MF entries, read once per launch.  Syncs.        */
+int32_t rmb_operator_work(rmb_operator* op, double* flops_per_state, double* op_bytes, void* stream);
 /* device time (ms, CUDA events on `stream`) spent inside matvec launches since the last reset, and
  * the number of launches it covers; enabling timing serialises with event syncs at query time only */
 int32_t rmb_matvec_timing(rmb_operator* op, int32_t enable, double* ms_out, int64_t* launches_out);

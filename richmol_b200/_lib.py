@@ -57,6 +57,7 @@ SYMBOLS = {
     "rmb_populations": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rmb_set_workspace_budget": (C.c_int32, [C.c_void_p, C.c_int64]),
     "rmb_get_counters": (C.c_int32, [C.c_void_p, c_i64p]),
+    "rmb_operator_work": (C.c_int32, [C.c_void_p, c_f64p, c_f64p, C.c_void_p]),
     "rmb_matvec_timing": (C.c_int32, [C.c_void_p, C.c_int32, c_f64p, c_i64p]),
 }
 

@@ -240,6 +240,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         pr.dm2 = d->blk_dm[h.ket];
         pr.nd = h.nd;
         pr.tab = h.tab;
+        op->h_prod_dm1.push_back(d->blk_dm[h.bra]);
+        op->h_prod_dk1.push_back(d->blk_dk[h.bra]);
         bra_begin[h.bra + 1]++;
     }
     for (int b = 0; b < d->nblocks; ++b) bra_begin[b + 1] += bra_begin[b];
@@ -1017,6 +1019,26 @@ int32_t rmb_get_counters(const rmb_operator* op, int64_t* out4) {
     out4[1] = op->n_matvec_launches;
     out4[2] = op->n_iterations;
     out4[3] = op->n_state_matvecs;
+    return RMB_OK;
+}
+
+int32_t rmb_operator_work(rmb_operator* op, double* flops_per_state, double* op_bytes, void* stream) {
+    if (!op) return RMB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<unsigned> mask((size_t)op->ntab + 1, 0u);
+    RMB_CUDA(cudaMemcpyAsync(mask.data(), op->d_tab_mask, sizeof(unsigned) * mask.size(), cudaMemcpyDeviceToHost, st));
+    RMB_CUDA(cudaStreamSynchronize(st));
+    double fl = 0, by = 0;
+    for (size_t p = 0; p < op->h_prods.size(); ++p) {
+        const ProdD& q = op->h_prods[p];
+        const double dm1 = op->h_prod_dm1[p], dk1 = op->h_prod_dk1[p];
+        const int nnz = __builtin_popcount(mask[q.tab]);
+        if (nnz == 0) continue;                       // the reference drops the block (field.py:1137-1139)
+        fl += (op->k_complex ? 8.0 : 4.0) * dm1 * dk1 * q.dk2 + 8.0 * nnz * dm1 * q.dk2;
+        by += (op->k_complex ? 16.0 : 8.0) * dk1 * q.dk2 + 20.0 * nnz * dm1;
+    }
+    if (flops_per_state) *flops_per_state = fl;
+    if (op_bytes) *op_bytes = by;
     return RMB_OK;
 }
 

@@ -88,6 +88,7 @@ struct rmb_operator {
     std::vector<rmb::PartH> parts;
     std::vector<rmb::ItemD> h_items;
     std::vector<rmb::ProdD> h_prods;
+    std::vector<int> h_prod_dm1, h_prod_dk1;   // bra dims per product (work accounting)
     size_t matvec_smem = 0;          // dynamic shared memory of the scalar matvec launch
     int matvec_S = 1;                // states per CTA (scalar kernel)
     // tiled matvec

@@ -263,3 +263,206 @@ def test_api_error_behaviour():
     out, _ = tdse.update(fresh, vecs + 1.0, H0=h0)   # with H0: phases only (tdse.py:377)
     ph = port.h0_phase(oracle_of(h0), EXP_FAC)
     assert relerr(out, (vecs + 1.0) * ph * ph) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# the BASELINE.json configurations at oracle-friendly sizes + size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _run_both(h0, H_gpu_builder, H_oracle_builder, fields, vecs0, tdse, use_h0=True):
+    oh = oracle_of(h0)
+    phase = port.h0_phase(oh, EXP_FAC) if use_h0 else None
+    v_gpu, v_or = vecs0.copy(), vecs0.copy()
+    for i, E in enumerate(fields):
+        orders = []
+        v_or = port.update_step(H_oracle_builder(E), v_or, EXP_FAC, phase=phase, orders=orders)
+        if use_h0:
+            v_gpu, _ = tdse.update(H_gpu_builder(E), v_gpu, H0=h0)
+        else:
+            v_gpu, _ = tdse.update(H_gpu_builder(E), v_gpu)
+        assert relerr(v_gpu, v_or) < TOL, i
+        assert list(tdse.last_orders) == orders, i
+    return v_gpu, v_or
+
+
+def test_config1_ocs_alignment_all_m():
+    """examples/ocs_alignment.py: linear rotor (dim_k = 1), Jmax = 30, all m (N = 961), T = 0, strong
+    800 nm Gaussian pulse with thresh = 1e3; steps around the pulse maximum and in its screened tail."""
+    m = synth.ocs(30)
+    h0, H = m["h0"], m["pol"] * (-0.5) * AUPOL
+    oH = oracle_of(m["pol"]).scaled(-0.5).scaled(AUPOL)
+    tdse = TDSE(t_start=0, t_end=300, dt=0.01)
+    tdse.time_grid()
+    vecs0 = tdse.init_state(h0, temp=0)
+    assert vecs0.shape == (1, 961)
+    omega = 2 * np.pi * 299792458.0 / 800e-9 * 1e-12
+
+    def field(t, fwhm=1.0):
+        t0 = 2.5 * fwhm / 2
+        return [0, 0, 1e10 * np.exp(-4 * np.log(2) * (t - t0) ** 2 / fwhm ** 2) * np.cos(omega * t)]
+    times = [1.25 + 0.01 * i for i in range(8)] + [0.02, 299.0]
+
+    def g(E):
+        H.field(E, thresh=1e3)
+        return H
+
+    def o(E):
+        oH.field(E, thresh=1e3)
+        return oH
+    _run_both(h0, g, o, [field(t) for t in times], vecs0, tdse)
+
+
+def test_config3_ocs_mixed_field_dressed_states():
+    """examples/ocs_mixed_field.py: dc field tilted in the XZ plane (M-mixing) contracted once, ac pulse
+    per step, lazy sum Hdc + Hac, initial states = eigenvectors of h0 + Hdc (dense eigh), cos / cos2."""
+    m = synth.ocs(8)
+    h0, dip, pol = m["h0"], m["dip"], m["pol"]
+    beta = 35.0 * np.pi / 180.0
+    dc = 20.7e5 * 50 * np.array([np.sin(beta), 0.0, np.cos(beta)])
+    Hdc = -1 * dip * dc * AUDIP
+    Hac = -0.5 * pol * AUPOL
+    tdse = TDSE(t_end=10, dt=0.01)
+    tdse.time_grid()
+    vecs0 = tdse.init_state(h0 + Hdc, temp=1.0)
+    odc = oracle_of(dip)
+    odc.field(dc)
+    odc = odc.scaled(-1).scaled(AUDIP)
+    oac = oracle_of(pol).scaled(-0.5).scaled(AUPOL)
+    ref0 = port.init_state(oracle_of(h0).add(odc), temp=1.0)
+    assert vecs0.shape == ref0.shape
+    # eigenvectors are defined up to a phase: compare projectors
+    assert relerr(np.abs(vecs0 @ ref0.conj().T), np.abs(ref0 @ ref0.conj().T)) < 1e-8
+    fields = [[0, 0, 1.5e9 * np.exp(-((i - 3) / 2.0) ** 2)] for i in range(6)]
+
+    def g(E):
+        Hac.field(E, thresh=1e1)
+        return Hdc + Hac
+
+    def o(E):
+        oac.field(E, thresh=1e1)
+        return odc.add(oac)
+    v_gpu, v_or = _run_both(h0, g, o, fields, ref0, tdse)
+    for name in ("cos", "cos2"):
+        O = m[name]
+        oc = oracle_of(O)
+        oc.field([0, 0, 1])
+        cm = oc.tomat()
+        ref = np.array([np.vdot(v, cm.dot(v)) for v in v_or])
+        assert relerr(expectation(O, v_gpu), ref) < TOL
+
+
+def test_config4_optical_centrifuge_complex_mf():
+    """Rotating polarisation E0 [cos(bt^2), sin(bt^2), 0]: xx, xy, yx, yy products, complex MF with
+    dm = 0, +-2 diagonals, asymmetric top; no H0 split on odd steps (full operator sum)."""
+    m = synth.h2s(5)
+    h0, pol = m["h0"], m["pol"] * (-0.5 * AUPOL)
+    opol = oracle_of(m["pol"]).scaled(-0.5 * AUPOL)
+    tdse = TDSE(t_end=10, dt=0.01)
+    tdse.time_grid()
+    vecs0 = tdse.init_state(h0, temp=10.0)[:40]
+    fields = [[4e9 * np.cos(0.3 * i * i), 4e9 * np.sin(0.3 * i * i), 0.0] for i in range(5)]
+
+    def g(E):
+        pol.field(E)
+        return pol
+
+    def o(E):
+        opol.field(E)
+        return opol
+    _run_both(h0, g, o, fields, vecs0, tdse)
+    # without H0=: exp(-i (H0 + V) dt) through the lazy sum with the rank-0 tensor
+    oh0 = oracle_of(h0)
+    _run_both(h0, lambda E: g(E) + h0, lambda E: o(E).add(oh0), fields[:2], vecs0, tdse, use_h0=False)
+
+
+def test_wide_k_blocks_column_chunks_and_row_tiles():
+    """dim_k > 12 (several column chunks per bra block) and dim_m = 2J+1 up to 53 (state tiles)."""
+    st = synth.asymmetric_rotor(*synth.H2S_ABC, 26, Jmin=24)
+    pol = synth.lab_tensor(synth.H2S_POL, st)
+    pol.field([1e9, -2e9, 3e9])
+    o = oracle_of(pol)
+    o.field([1e9, -2e9, 3e9])
+    N = pol._basis().N
+    assert max(pol._basis().dk) > 12
+    x = random_states(3, N, seed=4)
+    yo = np.array([port.flat_matvec(o, xi) for xi in x])
+    assert relerr(gpu_matvec(pol, x), yo) < 1e-13
+
+
+def test_complex_k_and_scalar_fallback_paths():
+    """K made complex by a complex scalar (field.py:939-944) runs the complex-K kernel; RMB_MATVEC=scalar
+    forces the general fallback kernel (and the unfused Lanczos path) -- both must match the oracle."""
+    import os
+    from richmol_b200.field import clear_device_cache
+    m = synth.h2o(4)
+    h0 = m["h0"]
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    vecs0 = tdse.init_state(h0, temp=30.0)[:9]
+    E = [1e9, 5e8, 2e9]
+    # complex K: not Hermitian any more, compare a plain matvec
+    polc = m["pol"] * (0.3 - 0.7j)
+    polc.field(E)
+    oc = oracle_of(m["pol"]).scaled(0.3 - 0.7j)
+    oc.field(E)
+    x = random_states(5, polc._basis().N, seed=6)
+    assert relerr(gpu_matvec(polc, x), np.array([port.flat_matvec(oc, xi) for xi in x])) < 1e-13
+    # scalar fallback
+    os.environ["RMB_MATVEC"] = "scalar"
+    clear_device_cache()
+    try:
+        pol = synth.h2o(4)["pol"] * (-0.5 * AUPOL)
+        opol = oracle_of(pol)
+
+        def g(E_):
+            pol.field(E_)
+            return pol
+
+        def o(E_):
+            opol.field(E_)
+            return opol
+        _run_both(h0, g, o, [E, [0, 0, 3e9]], vecs0, tdse)
+    finally:
+        del os.environ["RMB_MATVEC"]
+        clear_device_cache()
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (N = 12 341): properties that do not need the oracle."""
+    import torch
+    m = synth.h2o(20)
+    h0, dip, pol = m["h0"], m["dip"] * (-AUDIP), m["pol"] * (-0.5 * AUPOL)
+    N = h0._basis().N
+    assert N == 12341
+    dip.field([3e6, 0.0, 4e6])
+    pol.field([0.0, 0.0, 3e9], thresh=1e1)
+    H = dip + pol
+    x = random_states(6, N, seed=8)
+    y = gpu_matvec(H, x)
+    # linearity and Hermiticity of the assembled operator
+    a, b = 0.3 - 1.1j, -0.7 + 0.2j
+    assert relerr(gpu_matvec(H, (a * x[0] + b * x[1])[None, :])[0], a * y[0] + b * y[1]) < 1e-13
+    assert abs(np.vdot(x[2], y[3]) - np.conj(np.vdot(x[3], y[2]))) < 1e-12 * np.abs(y).max()
+    # one oracle matvec as an anchor
+    oH = oracle_of(dip)
+    oH.field([3e6, 0.0, 4e6])
+    op_ = oracle_of(pol)
+    op_.field([0.0, 0.0, 3e9], thresh=1e1)
+    assert relerr(y[0], port.flat_matvec(oH.add(op_), x[0])) < 1e-13
+    # propagation: unitarity (norms kept to the Lanczos tolerance), batch independence (a state gives
+    # bit-identical results alone or inside a batch), time-reversal (dt -> -dt undoes the step)
+    tdse = TDSE(t_end=10, dt=0.01)
+    tdse.time_grid()
+    vecs = torch.from_numpy(random_states(37, N, seed=9)).cuda()
+    out, _ = tdse.update(H, vecs, H0=h0)
+    orders = tdse.last_orders.copy()
+    assert orders.min() >= 2 and orders.max() < 30
+    n0 = torch.linalg.vector_norm(vecs, dim=1)
+    n1 = torch.linalg.vector_norm(out, dim=1)
+    assert float((n1 / n0 - 1).abs().max()) < 1e-7
+    alone, _ = tdse.update(H, vecs[5:6].clone(), H0=h0)
+    assert torch.equal(alone[0], out[5])
+    back = TDSE(t_end=10, dt=0.01)
+    back.time_grid()
+    back._dt = -0.01
+    rev, _ = back.update(H, out, H0=h0)
+    assert float((rev - vecs).abs().max()) < 1e-7
