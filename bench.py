@@ -31,12 +31,21 @@ METRIC = "state-timesteps/sec"
 UNIT = "state-steps/s"
 DT = 0.01            # ps
 NSTATES = 500        # states per GPU (weak scaling: the ensemble grows with the number of GPUs)
+NSTATES_BY_WORKLOAD = {"h2o": 500, "ocs": 8192}   # the linear-rotor case needs a batch larger than L2
 TEMP = 300.0         # K, Boltzmann weights of the shard rows
 
 
 # ------------------------------------------------------------------------------------------------
 # workload definition (shared by the GPU arm and the CPU arm)
 # ------------------------------------------------------------------------------------------------
+WORKLOAD_TEXT = {
+    "h2o": "h2o: H2O rigid rotor Watson-A Jmax=20 N={N}, {S}-state Boltzmann shard per GPU, dc dipole (tilted, "
+           "ramp) + ac polarisability, split-operator Lanczos step + <cos2theta>",
+    "ocs": "ocs: OCS linear rotor Jmax=60 N={N}, {S}-state shard per GPU, tilted dc dipole + ac polarisability "
+           "(M-mixing), split-operator Lanczos step + <cos2theta>",
+}
+
+
 def fields_at(step):
     """dc: 50 kV/cm tilted 35 deg in the XZ plane, ramped; ac: 800 nm Gaussian pulse along Z."""
     t = (step + 0.5) * DT
@@ -150,54 +159,81 @@ def cpu_run(workload, h0, steps, warmup, states_per_core, step0=0):
 # clocks sampling (B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md): an NVML polling
+    thread (10 ms period); falls back to an `nvidia-smi -lms` subprocess if pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, f"/tmp/rmb_clocks_{os.getpid()}.csv"
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.thread = self.proc = None
+        self.stop_flag = False
+
+    def _poll(self):
+        import pynvml
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            try:
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            # the physical index of the visible device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                self.index = int(vis.split(",")[self.index])
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            try:
+                self.path = f"/tmp/rmb_clocks_{os.getpid()}.csv"
+                self.f = open(self.path, "w")
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20",
+                     "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            except OSError:
+                self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.f.close()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                try:
+                    self.samples.append(float(p[0]))
+                    self.max_mhz = float(p[1])
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
             os.remove(self.path)
-        except OSError:
-            pass
-        return out
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -227,7 +263,7 @@ def gpu_run(args):
     tdse.time_grid = lambda *a, **k: None                      # open-ended grid for the benchmark
     tdse._time_grid = (None, _Endless(DT), None)
     vecs = torch.from_numpy(rows).to(dev)
-    obs = torch.zeros(2, dtype=torch.complex128, device=dev)
+    obs = torch.zeros(1, dtype=torch.complex128, device=dev)
 
     def step(i, v):
         dc, ac = fields_at(i)
@@ -235,10 +271,9 @@ def gpu_run(args):
         Hac.field(ac, thresh=1e1)
         v, _ = tdse.update(Hdc + Hac, v, H0=h0, inplace=True)
         ev = expectation(cos2, v)
-        obs[0] = ev.sum()
-        obs[1] = (v.real ** 2 + v.imag ** 2).sum()
+        torch.sum(ev, dim=0, keepdim=True, out=obs)            # ensemble <cos^2 theta> - 1/3 of this shard
         if world > 1:
-            dist.all_reduce(obs)                               # the path's only collective
+            dist.all_reduce(torch.view_as_real(obs))           # the path's only collective
         return v
 
     def barrier():
@@ -310,9 +345,7 @@ def gpu_run(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: H2O rigid rotor Watson-A Jmax=20 N={N}, {NSTATES}-state "
-                               f"Boltzmann shard per GPU, dc dipole (tilted, ramp) + ac polarisability, "
-                               f"split-operator Lanczos step + <cos2theta>",
+        "config": {"workload": WORKLOAD_TEXT[args.workload].format(N=N, S=NSTATES),
                    "states_per_gpu": NSTATES, "hilbert_dim": N, "dt_ps": DT,
                    "parallelism": f"ensemble-sharded x{world}",
                    "l2": "working set (Psi + Krylov vectors, ~0.6 GB per GPU) larger than the 126 MB L2"},
@@ -389,15 +422,17 @@ def e2e_run(args, tdse, Hdc, Hac, h0, cos2, rows, world, dev):
 
 
 def main():
+    global NSTATES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="h2o", choices=["h2o", "ocs"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-states-per-core", type=int, default=2)
     args = ap.parse_args()
+    NSTATES = NSTATES_BY_WORKLOAD[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
 

@@ -108,7 +108,9 @@ int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t
  *     psi <- ph * exp(fac * H) * (ph * psi)          ph = h0phase_dev (may be NULL: no split)
  * with the reference's recurrences and stopping rule (sum |u_k - u_{k-1}|^2 <= tol, at most
  * `maxorder` basis vectors).  orders_host (may be NULL) receives per state the index of the last
- * Lanczos iteration (= matvecs - 1).  Returns RMB_ERR_MAXORDER if any state reached maxorder.
+ * Lanczos iteration (= matvecs - 1); the copy is enqueued on `stream` -- synchronise the stream before
+ * reading it (pinned memory keeps the call asynchronous).  Returns RMB_ERR_MAXORDER if any state
+ * reached maxorder (known without a final synchronisation: the flag is raised when a state retires).
  * If `skip_krylov` != 0 only the two phase multiplications are applied (richmol/tdse.py:377).        */
 int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld,
                            double fac_re, double fac_im, double tol, int32_t maxorder,

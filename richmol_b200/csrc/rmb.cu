@@ -801,8 +801,10 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     op->n_state_matvecs += B;
     for (long long a : act_hist) op->n_state_matvecs += a;
     if (orders_host) {
+        // asynchronous: the caller synchronises the stream before reading (rmb_propagate_step documents
+        // this; the Python layer reads `last_orders` lazily).  Pageable destinations make the copy
+        // synchronous, pinned ones do not.
         RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-        RMB_CUDA(cudaStreamSynchronize(st));
     }
     return RMB_OK;
 }

@@ -197,6 +197,19 @@ class TDSE():
             self._cache["phase_dev"] = hit
         return hit[1]
 
+    @property
+    def last_orders(self):
+        """Per-state index of the last Lanczos iteration of the latest `update` (= matvecs - 1).  For
+        device-resident ensembles the values are copied back asynchronously; reading them waits for
+        the step to finish."""
+        o = getattr(self, "_orders", None)
+        if isinstance(o, tuple):
+            pin, nst, stream = o
+            stream.synchronize()
+            o = pin[:nst].numpy().copy()
+            self._orders = o
+        return o
+
     @update_counter
     def update(self, H, vecs, **kwargs):
         """Propagates vectors by one time-step (richmol/tdse.py:265-414).
@@ -261,7 +274,7 @@ class TDSE():
                 from .field import DeviceOperator
                 op = DeviceOperator(H._basis(), [])
                 self._cache["phase_only_op"] = op
-        self.last_orders = None
+        self._orders = None
 
         try:
             import torch
@@ -278,12 +291,16 @@ class TDSE():
             if not out.is_contiguous():
                 raise ValueError("device `vecs` must be contiguous")
             nst = out.shape[0]
-            orders = np.zeros(nst, dtype=np.int32)
+            # pinned buffer: the order copy is enqueued, not waited for (see `last_orders`)
+            pin = self._cache.get("orders_pin")
+            if pin is None or pin.numel() < nst:
+                pin = torch.zeros(max(nst, 1), dtype=torch.int32).pin_memory()
+                self._cache["orders_pin"] = pin
             ph_ptr = self._h0_phase_device(out.device).data_ptr() if phase is not None else None
             status = lib.rmb_propagate_step(
                 op.handle, out.data_ptr(), nst, N, exp_fac.real, exp_fac.imag, float(tol), 100,
-                ph_ptr, int(skip), orders.ctypes.data, stream)
-            self.last_orders = orders
+                ph_ptr, int(skip), pin.data_ptr(), stream)
+            self._orders = (pin, nst, torch.cuda.current_stream(out.device))
             _lib.check(status)
             return out
 
@@ -305,7 +322,7 @@ class TDSE():
             op.handle, vin.ctypes.data, vout.ctypes.data, nst, N, exp_fac.real, exp_fac.imag,
             float(tol), 100, ph.ctypes.data if ph is not None else None, int(skip),
             orders.ctypes.data, stream)
-        self.last_orders = orders
+        self._orders = orders
         _lib.check(status)
         return vout
 
