@@ -324,7 +324,7 @@ def gpu_run(args):
     roofline = {
         "kernel": "k_matvec (H.Psi, fused MF(x)K block products)",
         "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+        "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload), "peak_source": peaks["source"],
         "launches": int(mv_launches), "avg_launch_us": mv_s / mv_launches * 1e6,
         "share_of_step": mv_s * 1e3 / ms,
         "fp64": {"achieved_tflops": alg_flops / mv_s / 1e12 if mv_s > 0 else 0.0, "peak_tflops": 37.2,
@@ -369,6 +369,18 @@ def op_info(op):
     fl, by = C.c_double(), C.c_double()
     _lib.check(_lib.lib().rmb_operator_work(op.handle, C.byref(fl), C.byref(by), None))
     return {"flops_per_state": fl.value, "op_bytes": by.value}
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one full matvec launch from the committed ncu capture
+    (profiles/), bytes per launch; None if no capture exists for this workload."""
+    if workload != "h2o":
+        return None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")))
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
