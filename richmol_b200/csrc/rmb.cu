@@ -10,6 +10,7 @@
 
 #include "rmb_kernels.cuh"
 #include "rmb_matvec.cuh"
+#include "rmb_fused.cuh"
 
 namespace rmb {
 
@@ -58,6 +59,10 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_prods);
     cudaFree(op->d_items);
     cudaFree(op->d_pmap);
+    cudaFree(op->d_row_blk);
+    cudaFree(op->d_blk_begin);
+    cudaFree(op->d_blk_off);
+    cudaFree(op->d_blk_dm);
     cudaFree(op->d_items2);
     cudaFree(op->d_gdesc);
     cudaFree(op->d_ktpool);
@@ -454,6 +459,31 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     if ((rc = upload(&op->d_prods, op->h_prods.data(), op->h_prods.size()))) return rc;
     if ((rc = upload(&op->d_items, op->h_items.data(), op->h_items.size()))) return rc;
     if ((rc = upload((Item2D**)&op->d_items2, items2.data(), items2.size()))) return rc;
+    // fused single-launch step: every block has dim_k = 1 and three vectors fit in shared memory
+    {
+        bool all1 = true;
+        for (int b = 0; b < d->nblocks; ++b) all1 = all1 && d->blk_dk[b] == 1;
+        const size_t fused_smem = (size_t)3 * op->n * sizeof(cplx);
+        if (all1 && fused_smem <= 200 * 1024 && op->nd_max <= 32) {
+            std::vector<int> row_blk((size_t)op->n);
+            std::vector<long long> boff(d->nblocks);
+            for (int b = 0; b < d->nblocks; ++b) {
+                boff[b] = d->blk_off[b];
+                for (long long i = d->blk_off[b]; i < d->blk_off[b + 1]; ++i) row_blk[(size_t)i] = b;
+            }
+            if ((rc = upload(&op->d_row_blk, row_blk.data(), row_blk.size()))) return rc;
+            if ((rc = upload(&op->d_blk_begin, bra_begin.data(), bra_begin.size()))) return rc;
+            if ((rc = upload(&op->d_blk_off, boff.data(), boff.size()))) return rc;
+            if ((rc = upload(&op->d_blk_dm, d->blk_dm, (size_t)d->nblocks))) return rc;
+            static size_t g_fused_smem = 16 * 1024;   // 13 KB of static shared memory come on top
+            if (fused_smem > g_fused_smem) {
+                RMB_CUDA(cudaFuncSetAttribute(k_lanczos_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+                g_fused_smem = fused_smem;
+            }
+            const char* ff = getenv("RMB_FUSED");
+            op->fused_ok = !(ff && strcmp(ff, "0") == 0);
+        }
+    }
     if ((rc = upload((ProdS**)&op->d_gdesc, gdesc.data(), gdesc.size()))) return rc;
     ktpool.push_back(0.0);
     ktpool.push_back(0.0);
@@ -832,6 +862,49 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
     if (maxorder < 1 || maxorder > MAX_ORDER_SMEM) {
         set_error("maxorder must be in [1, 128]");
         return RMB_ERR_INVALID;
+    }
+    // small linear-rotor problems: the whole step in one launch (rmb_fused.cuh)
+    if (op->fused_ok && nstates <= 65535 &&
+        (long long)nstates * n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30)) {
+        if ((rc = ensure_workspace(op, nstates, maxorder))) return rc;
+        if ((rc = ensure_slab(op, maxorder, st))) return rc;
+        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
+        FusedArgs fa;
+        fa.n = n;
+        fa.row_blk = op->d_row_blk;
+        fa.blk_begin = op->d_blk_begin;
+        fa.blk_off = op->d_blk_off;
+        fa.blk_dm = op->d_blk_dm;
+        fa.prods = op->d_prods;
+        fa.tab_mask = op->d_tab_mask;
+        fa.cent = (const MfEntry*)op->d_ent_cent;
+        fa.kpool = op->d_kpool;
+        fa.k_complex = op->k_complex ? 1 : 0;
+        fa.slabs = op->d_slab_ptrs;
+        fa.fac = fac;
+        fa.tol = tol;
+        fa.maxorder = maxorder;
+        fa.ph = ph;
+        fa.psi = psi;
+        fa.ld = ld;
+        fa.order = op->d_order;
+        fa.ctrl = op->d_ctrl;
+        // the history slabs are indexed [slab][state * n + i] with the leading dimension of this batch
+        k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS, (size_t)3 * n * sizeof(cplx), st>>>(fa, nstates);
+        RMB_CUDA(cudaGetLastError());
+        op->n_launches++;
+        op->n_iterations++;
+        if (orders_host)
+            RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * nstates, cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if (op->h_ctrl[0]) {
+            char buf[128];
+            snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
+            set_error(buf);
+            return RMB_ERR_MAXORDER;
+        }
+        return RMB_OK;
     }
     // sub-batch size from the workspace budget: the product vector and ~15 Krylov vectors per state
     long long bc = op->ws_states;

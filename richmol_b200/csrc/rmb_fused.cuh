@@ -1,0 +1,233 @@
+// K3 (fused, small Hilbert spaces): one whole split-operator Lanczos step per launch.
+//
+// One CTA per ensemble member.  The three live vectors of the recurrence (V_{k-1}, V_k, w) stay in shared
+// memory for the whole step, the Krylov history V_0..V_k goes to a global (L2-resident) slab only for the
+// convergence metric and the final combination, the small exponential exp(fac*T_k) e_0 is evaluated by one
+// warp in shared memory, and every inner product is a fixed-order block reduction.  No host round trip
+// per Lanczos iteration: this is the path for the reference's latency-bound cases (OCS alignment with a
+// single state, 1 K ensembles with tens of states; examples/ocs_alignment.py, ocs_mixed_field.py).
+// Restricted to operators whose (J,sym) blocks all have dim_k = 1 (linear rotors) and N*48 B of shared
+// memory; everything else takes the batched path (rmb.cu: lanczos_batch).
+//
+// Arithmetic follows tdse.py:417-486 literally, including V_k = W_{k-1} / beta_k by division.
+#pragma once
+#include "rmb_kernels.cuh"
+#include "rmb_matvec.cuh"
+
+namespace rmb {
+
+constexpr int FUSED_THREADS = 512;
+
+struct FusedArgs {
+    long long n;                 // Hilbert-space dimension (= padded length: dim_k = 1 everywhere)
+    const int* row_blk;          // [n] (J,sym) block of the row
+    const int* blk_begin;        // [nblocks + 1] products of the block (sorted by bra)
+    const long long* blk_off;    // [nblocks] offset of the block
+    const int* blk_dm;           // [nblocks]
+    const ProdD* prods;
+    const unsigned* tab_mask;
+    const MfEntry* cent;
+    const double* kpool;
+    int k_complex;
+    cplx* const* slabs;          // [maxorder + 1] history, each nstates * n
+    cplx fac;
+    double tol;
+    int maxorder;
+    const cplx* ph;              // H0 phase (may be null)
+    cplx* psi;                   // in/out, state-major with leading dimension ld
+    long long ld;
+    int* order;                  // [nstates]
+    int* ctrl;                   // [1] maxorder flag
+};
+
+template <int NT>
+__device__ __forceinline__ double block_sum_all(double v, double* sm) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) r += sm[i];
+    return r;                     // same value in every thread, fixed order
+}
+
+// y = H x for one state, x and y in shared memory (dim_k = 1: H = sum_p k_p MF_p)
+__device__ __forceinline__ void fused_matvec(const FusedArgs& a, const cplx* __restrict__ x, cplx* __restrict__ y) {
+    for (long long i = threadIdx.x; i < a.n; i += FUSED_THREADS) {
+        const int b = a.row_blk[i];
+        const int m1 = (int)(i - a.blk_off[b]);
+        const int dm1 = a.blk_dm[b];
+        cplx acc = make_double2(0.0, 0.0);
+        for (int p = a.blk_begin[b]; p < a.blk_begin[b + 1]; ++p) {
+            const ProdD pr = a.prods[p];
+            const int nnz = __popc(a.tab_mask[pr.tab]);
+            cplx z = make_double2(0.0, 0.0);
+            for (int q = 0; q < nnz; ++q) {
+                const MfEntry e = a.cent[pr.ent_off + (long long)q * dm1 + m1];
+                if (e.col >= 0) {
+                    const cplx v = x[pr.ket_off + e.col];
+                    z.x = fma(e.re, v.x, z.x);
+                    z.y = fma(e.re, v.y, z.y);
+                    z.x = fma(-e.im, v.y, z.x);
+                    z.y = fma(e.im, v.x, z.y);
+                }
+            }
+            if (a.k_complex) {
+                const cplx kv = reinterpret_cast<const cplx*>(a.kpool)[pr.koff];
+                cfma(acc, kv, z);
+            } else {
+                const double kv = a.kpool[pr.koff];
+                acc.x = fma(kv, z.x, acc.x);
+                acc.y = fma(kv, z.y, acc.y);
+            }
+        }
+        y[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+k_lanczos_fused(const FusedArgs a, long long nstates) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* vk = reinterpret_cast<cplx*>(smem_raw);       // V_k
+    cplx* vkm1 = vk + a.n;                              // V_{k-1}
+    cplx* w = vkm1 + a.n;                               // H V_k, then W_k
+    __shared__ double red[FUSED_THREADS / 32];
+    __shared__ double2 s_alpha[MAX_ORDER_SMEM];
+    __shared__ double s_beta[MAX_ORDER_SMEM + 1];
+    __shared__ double2 s_c[MAX_ORDER_SMEM], s_dc[MAX_ORDER_SMEM];
+    __shared__ double2 s_y[MAX_ORDER_SMEM], s_t1[MAX_ORDER_SMEM], s_t2[MAX_ORDER_SMEM];
+    const long long s = blockIdx.x;
+    cplx* psi = a.psi + s * a.ld;
+    const long long n = a.n;
+
+    // V_0 = psi * ph (not normalised, tdse.py:443 / 375)
+    for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+        cplx v = psi[i];
+        if (a.ph) v = cmul(v, a.ph[i]);
+        vk[i] = v;
+        a.slabs[0][s * n + i] = v;
+    }
+    if (threadIdx.x == 0) { s_c[0] = make_double2(1.0, 0.0); s_beta[0] = 0.0; }
+    __syncthreads();
+
+    int k = 0, last = 0;
+    bool hit_max = (a.maxorder <= 1);
+    for (;; ++k) {
+        // w = H V_k ; alpha_k = vdot(w, V_k)
+        fused_matvec(a, vk, w);
+        __syncthreads();
+        double re = 0, im = 0;
+        for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+            const cplx x = w[i], y = vk[i];
+            re += x.x * y.x + x.y * y.y;
+            im += x.x * y.y - x.y * y.x;
+        }
+        re = block_sum_all<FUSED_THREADS>(re, red);
+        im = block_sum_all<FUSED_THREADS>(im, red);
+        const cplx alpha = make_double2(re, im);
+        const double beta = s_beta[k];
+        if (threadIdx.x == 0) s_alpha[k] = alpha;
+        // W_k = w - alpha V_k - beta V_{k-1}; norm
+        double nr = 0;
+        for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+            cplx r = csub(w[i], cmul(alpha, vk[i]));
+            if (k > 0) { r.x -= beta * vkm1[i].x; r.y -= beta * vkm1[i].y; }
+            w[i] = r;
+            nr += cabs2(r);
+        }
+        nr = block_sum_all<FUSED_THREADS>(nr, red);
+        const double beta_next = sqrt(nr);
+        if (threadIdx.x == 0) s_beta[k + 1] = beta_next;
+        __syncthreads();
+        bool done = false;
+        if (k > 0) {
+            // c^k = expm(fac T_k) e_0 ; conv = sum |sum_i (c^k_i - c^{k-1}_i) V_i|^2
+            if (threadIdx.x < 32) {
+                warp_expm_col0(k + 1, s_alpha, s_beta, a.fac, s_y, s_t1, s_t2);
+                for (int i = threadIdx.x; i <= k; i += 32) {
+                    const cplx prev = (i < k) ? s_c[i] : make_double2(0.0, 0.0);
+                    s_dc[i] = csub(s_y[i], prev);
+                    s_c[i] = s_y[i];
+                }
+            }
+            __syncthreads();
+            double cv = 0;
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                cplx d = make_double2(0.0, 0.0);
+                for (int j = 0; j + 2 <= k; ++j) cfma(d, s_dc[j], a.slabs[j][s * n + i]);
+                cfma(d, s_dc[k - 1], vkm1[i]);
+                cfma(d, s_dc[k], vk[i]);
+                cv += cabs2(d);
+            }
+            cv = block_sum_all<FUSED_THREADS>(cv, red);
+            last = k;
+            if (k == a.maxorder - 1) { hit_max = true; done = true; }
+            else if (!(cv > a.tol)) done = true;
+        } else if (a.maxorder <= 1) {
+            done = true;
+        }
+        if (done) break;
+        // V_{k+1} = W_k / beta_{k+1}, or the Gram-Schmidt fallback when beta_{k+1} == 0 (tdse.py:455-465)
+        if (beta_next != 0.0) {
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                const cplx r = w[i];
+                vkm1[i] = vk[i];
+                const cplx v = make_double2(r.x / beta_next, r.y / beta_next);
+                vk[i] = v;
+                a.slabs[k + 1][s * n + i] = v;
+            }
+        } else {
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                vkm1[i] = vk[i];
+                w[i] = make_double2(1.0, 0.0);
+            }
+            __syncthreads();
+            for (int j = 0; j <= k; ++j) {
+                double pr = 0, pi = 0;
+                for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                    const cplx x = (j == k) ? vkm1[i] : a.slabs[j][s * n + i], y = w[i];
+                    pr += x.x * y.x + x.y * y.y;
+                    pi += x.x * y.y - x.y * y.x;
+                }
+                pr = block_sum_all<FUSED_THREADS>(pr, red);
+                pi = block_sum_all<FUSED_THREADS>(pi, red);
+                const cplx proj = make_double2(pr, pi);
+                for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                    const cplx x = (j == k) ? vkm1[i] : a.slabs[j][s * n + i];
+                    w[i] = csub(w[i], cmul(proj, x));
+                }
+                __syncthreads();
+            }
+            double nv = 0;
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) nv += cabs2(w[i]);
+            nv = sqrt(block_sum_all<FUSED_THREADS>(nv, red));
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                const cplx v = make_double2(w[i].x / nv, w[i].y / nv);
+                vk[i] = v;
+                a.slabs[k + 1][s * n + i] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // psi = ph * u_k,  u_k = sum_i c_i V_i  (u_0 = V_0 when the loop never ran)
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+        cplx u = make_double2(0.0, 0.0);
+        if (last == 0) {
+            u = a.slabs[0][s * n + i];
+        } else {
+            for (int j = 0; j + 2 <= last; ++j) cfma(u, s_c[j], a.slabs[j][s * n + i]);
+            cfma(u, s_c[last - 1], vkm1[i]);
+            cfma(u, s_c[last], vk[i]);
+        }
+        psi[i] = a.ph ? cmul(u, a.ph[i]) : u;
+    }
+    if (threadIdx.x == 0) {
+        a.order[s] = last;
+        if (hit_max) atomicExch(a.ctrl, 1);
+    }
+}
+
+}  // namespace rmb

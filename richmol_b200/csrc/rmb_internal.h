@@ -110,6 +110,13 @@ struct rmb_operator {
     double flops_per_state = 0;
     double op_bytes = 0;
 
+    // ---- fused single-launch Lanczos step (linear rotors, small N): row -> block tables
+    bool fused_ok = false;
+    int* d_row_blk = nullptr;
+    int* d_blk_begin = nullptr;
+    long long* d_blk_off = nullptr;
+    int* d_blk_dm = nullptr;
+
     // ---- Krylov workspace (lazily sized) ----
     long long ws_budget = 0;         // bytes; 0 = auto
     long long ws_states = 0;         // capacity in states of each slab
