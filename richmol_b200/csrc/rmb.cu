@@ -539,7 +539,14 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
     }
     cudaStream_t st = (cudaStream_t)stream;
     PartH& ph = op->parts[part];
-    RMB_CUDA(cudaMemcpyAsync(ph.d_fprod, fprod, sizeof(double) * ph.ncart, cudaMemcpyHostToDevice, st));
+    FieldProds fp;
+    const double* fdev = nullptr;
+    if (ph.ncart <= 16) {
+        for (int c = 0; c < 16; ++c) fp.f[c] = c < ph.ncart ? fprod[c] : 0.0;
+    } else {
+        RMB_CUDA(cudaMemcpyAsync(ph.d_fprod, fprod, sizeof(double) * ph.ncart, cudaMemcpyHostToDevice, st));
+        fdev = ph.d_fprod;
+    }
     const long long nent = ph.ent_end - ph.ent_begin;
     RMB_CUDA(cudaMemsetAsync(op->d_flags + 1 + part, 0, sizeof(int), st));
     if (ph.tab_end > ph.tab_begin)
@@ -547,7 +554,7 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
     if (nent > 0) {
         const int nt = 256;
         k_field_contract<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
-            nent, ph.ncart, ph.d_coef, ph.d_fprod, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
+            nent, ph.ncart, ph.d_coef, fdev, fp, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
             op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, ph.ent_begin);
         k_compact_tables<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ent_begin, op->d_ent_val, op->d_ent_col, op->d_ent_tab, op->d_tab_off, op->d_tab_nd,

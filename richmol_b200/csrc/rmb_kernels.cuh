@@ -62,8 +62,10 @@ __device__ __forceinline__ double warp_reduce_partials(const double* p, int n, i
 // ------------------------------------------------------------------------------------------
 // K1: field contraction  MF[e] = sum_c f[c] * M_c[e], element threshold (field.py:1122-1139)
 // ------------------------------------------------------------------------------------------
+struct FieldProds { double f[16]; };   // products of field components by value (ncart <= 9 for rank <= 2)
+
 __global__ void k_field_contract(long long nent, int ncart, const cplx* __restrict__ coef,
-                                 const double* __restrict__ fprod, double thresh, int all_dropped,
+                                 const double* __restrict__ fprod_dev, const FieldProds fp, double thresh, int all_dropped,
                                  cplx* __restrict__ val, int* __restrict__ nz_flag,
                                  const int* __restrict__ ent_tab, const int* __restrict__ tab_off,
                                  const int* __restrict__ tab_nd, unsigned* __restrict__ tab_mask,
@@ -73,7 +75,7 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
     cplx acc = make_double2(0.0, 0.0);
     if (!all_dropped) {
         for (int c = 0; c < ncart; ++c) {
-            const double f = fprod[c];
+            const double f = fprod_dev ? fprod_dev[c] : fp.f[c];
             if (f != 0.0) {
                 const cplx m = coef[(long long)c * nent + e];
                 acc.x += f * m.x;

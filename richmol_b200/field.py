@@ -319,10 +319,13 @@ class CarTens:
         at the time of the addition and whose irrep keys are renamed '<irrep>_1' / '<irrep>_2'."""
         if not isinstance(arg, CarTens):
             raise TypeError(f"bad argument type for `arg`: '{type(arg)}'") from None
-        bad = [a for a in _BASIS_ATTRS if getattr(self, a) != getattr(arg, a)]
-        if bad:
-            raise ValueError(
-                f"tensors defined with respect to different basis sets (differ in {bad})") from None
+        # same check as the reference (field.py:967-986), done on the cached block layout first
+        b1, b2 = self.__dict__.get("_basis_cache"), arg.__dict__.get("_basis_cache")
+        if b1 is None or b2 is None or (b1 is not b2 and b1.key() != b2.key()):
+            bad = [a for a in _BASIS_ATTRS if getattr(self, a) != getattr(arg, a)]
+            if bad:
+                raise ValueError(
+                    f"tensors defined with respect to different basis sets (differ in {bad})") from None
         for t in (self, arg):
             try:
                 if t.cart[0] == "0":

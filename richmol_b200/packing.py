@@ -31,7 +31,11 @@ class Basis:
         self.N = int(self.off[-1])
 
     def key(self):
-        return (tuple(self.blocks), self.dm.tobytes(), self.dk.tobytes())
+        k = self.__dict__.get("_key")
+        if k is None:
+            k = (tuple(self.blocks), self.dm.tobytes(), self.dk.tobytes())
+            self.__dict__["_key"] = k
+        return k
 
     @classmethod
     def of(cls, tens, side=2):
@@ -220,26 +224,34 @@ def _ell_table(dm1, dm2, coos, ncart):
     return col, coef, nd
 
 
+_AXIS = {"x": 0, "y": 1, "z": 2}
+_CART_IDX = {}
+
+
 def field_products(cart, field, thresh):
     """Products of field components per Cartesian label with the product screening of
     CarTens.field (richmol/field.py:1094-1105).  Returns (fprod[ncart], all_dropped)."""
     try:
         fx, fy, fz = field[:3]
-        fxyz = np.array([fx, fy, fz])
+        f = (float(fx), float(fy), float(fz))
     except (TypeError, IndexError, ValueError):
         raise IndexError(
             "field variable must be an iterable with three items which represent field's X, Y, "
             "and Z components") from None
-    axis = {"x": 0, "y": 1, "z": 2}
-    fprod = np.zeros(len(cart), dtype=np.float64)
+    key = tuple(cart)
+    idx = _CART_IDX.get(key)
+    if idx is None:
+        idx = [None if c == "0" else tuple(_AXIS[ch] for ch in c) for c in cart]
+        _CART_IDX[key] = idx
+    fprod = [0.0] * len(idx)
     kept = 0
-    for i, c in enumerate(cart):
-        if c == "0":
-            val = 1
-        else:
-            val = np.prod(fxyz[[axis[ch] for ch in c]])
+    for i, ax in enumerate(idx):
+        val = 1.0
+        if ax is not None:
+            for a in ax:
+                val *= f[a]
         if thresh is not None and not abs(val) >= thresh:
             continue
         fprod[i] = val
         kept += 1
-    return fprod, kept == 0
+    return np.array(fprod, dtype=np.float64), kept == 0

@@ -177,7 +177,12 @@ class TDSE():
 
     # ------------------------------------------------------------------------------------------
     def _exp_fac(self):
-        return -1j * self._dt * self._t_to_s * self._enr_to_J / const.value("reduced Planck constant")
+        key = (self._dt, self._t_to_s, self._enr_to_J)
+        hit = self._cache.get("exp_fac")
+        if hit is None or hit[0] != key:
+            hit = (key, -1j * self._dt * self._t_to_s * self._enr_to_J / const.value("reduced Planck constant"))
+            self._cache["exp_fac"] = hit
+        return hit[1]
 
     def _h0_phase(self, H0, exp_fac):
         """exp(exp_fac/2 * diag(H0)), cached on first use like the reference (richmol/tdse.py:368-373)."""
