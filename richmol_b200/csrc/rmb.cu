@@ -463,8 +463,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     {
         bool all1 = true;
         for (int b = 0; b < d->nblocks; ++b) all1 = all1 && d->blk_dk[b] == 1;
-        const size_t fused_smem = (size_t)3 * op->n * sizeof(cplx);
-        if (all1 && fused_smem <= 200 * 1024 && op->nd_max <= 32) {
+        const size_t fused_smem = (size_t)3 * op->n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd);
+        if (all1 && fused_smem <= 210 * 1024 && op->nd_max <= 32 && op->nent < (1LL << 31)) {
             std::vector<int> row_blk((size_t)op->n);
             std::vector<long long> boff(d->nblocks);
             for (int b = 0; b < d->nblocks; ++b) {
@@ -887,6 +887,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         fa.cent = (const MfEntry*)op->d_ent_cent;
         fa.kpool = op->d_kpool;
         fa.k_complex = op->k_complex ? 1 : 0;
+        fa.nprod = op->nprod;
         fa.slabs = op->d_slab_ptrs;
         fa.fac = fac;
         fa.tol = tol;
@@ -897,7 +898,8 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         fa.order = op->d_order;
         fa.ctrl = op->d_ctrl;
         // the history slabs are indexed [slab][state * n + i] with the leading dimension of this batch
-        k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS, (size_t)3 * n * sizeof(cplx), st>>>(fa, nstates);
+        k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS,
+                          (size_t)3 * n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd), st>>>(fa, nstates);
         RMB_CUDA(cudaGetLastError());
         op->n_launches++;
         op->n_iterations++;

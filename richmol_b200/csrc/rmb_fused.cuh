@@ -29,6 +29,7 @@ struct FusedArgs {
     const MfEntry* cent;
     const double* kpool;
     int k_complex;
+    int nprod;
     cplx* const* slabs;          // [maxorder + 1] history, each nstates * n
     cplx fac;
     double tol;
@@ -53,35 +54,50 @@ __device__ __forceinline__ double block_sum_all(double v, double* sm) {
     return r;                     // same value in every thread, fixed order
 }
 
-// y = H x for one state, x and y in shared memory (dim_k = 1: H = sum_p k_p MF_p)
-__device__ __forceinline__ void fused_matvec(const FusedArgs& a, const cplx* __restrict__ x, cplx* __restrict__ y) {
+// compact per-product descriptor kept in shared memory for the whole step
+struct FusedProd {
+    int ket_off;         // offset of the ket block in the state vector
+    int ent_off;         // first compacted MF entry of the table
+    int nnz;             // diagonals that survived the field contraction
+    int pad;
+    double kre, kim;     // the 1 x 1 K factor
+};
+
+// y = H x for one state, x and y in shared memory (dim_k = 1: H = sum_p k_p MF_p).  The <= 5 entries of a
+// product are fetched with independent loads (memory-level parallelism: the entries stream from L2).
+__device__ __forceinline__ void fused_matvec(const FusedArgs& a, const FusedProd* __restrict__ sp,
+                                             const cplx* __restrict__ x, cplx* __restrict__ y) {
     for (long long i = threadIdx.x; i < a.n; i += FUSED_THREADS) {
         const int b = a.row_blk[i];
         const int m1 = (int)(i - a.blk_off[b]);
         const int dm1 = a.blk_dm[b];
         cplx acc = make_double2(0.0, 0.0);
-        for (int p = a.blk_begin[b]; p < a.blk_begin[b + 1]; ++p) {
-            const ProdD pr = a.prods[p];
-            const int nnz = __popc(a.tab_mask[pr.tab]);
+        const int p1 = a.blk_begin[b + 1];
+        for (int p = a.blk_begin[b]; p < p1; ++p) {
+            const FusedProd pr = sp[p];
+            const MfEntry* ep = a.cent + pr.ent_off + m1;
+            MfEntry e[MV2_NDMAX];
+#pragma unroll
+            for (int q = 0; q < MV2_NDMAX; ++q)
+                if (q < pr.nnz) e[q] = ep[(long long)q * dm1];
             cplx z = make_double2(0.0, 0.0);
-            for (int q = 0; q < nnz; ++q) {
-                const MfEntry e = a.cent[pr.ent_off + (long long)q * dm1 + m1];
-                if (e.col >= 0) {
-                    const cplx v = x[pr.ket_off + e.col];
-                    z.x = fma(e.re, v.x, z.x);
-                    z.y = fma(e.re, v.y, z.y);
-                    z.x = fma(-e.im, v.y, z.x);
-                    z.y = fma(e.im, v.x, z.y);
+#pragma unroll
+            for (int q = 0; q < MV2_NDMAX; ++q)
+                if (q < pr.nnz && e[q].col >= 0) {
+                    const cplx v = x[pr.ket_off + e[q].col];
+                    z.x = fma(e[q].re, v.x, z.x);
+                    z.y = fma(e[q].re, v.y, z.y);
+                    z.x = fma(-e[q].im, v.y, z.x);
+                    z.y = fma(e[q].im, v.x, z.y);
                 }
+            for (int q = MV2_NDMAX; q < pr.nnz; ++q) {      // rank > 2 tensors: plain loop
+                const MfEntry eq = ep[(long long)q * dm1];
+                if (eq.col >= 0) cfma(z, make_double2(eq.re, eq.im), x[pr.ket_off + eq.col]);
             }
-            if (a.k_complex) {
-                const cplx kv = reinterpret_cast<const cplx*>(a.kpool)[pr.koff];
-                cfma(acc, kv, z);
-            } else {
-                const double kv = a.kpool[pr.koff];
-                acc.x = fma(kv, z.x, acc.x);
-                acc.y = fma(kv, z.y, acc.y);
-            }
+            acc.x = fma(pr.kre, z.x, acc.x);
+            acc.y = fma(pr.kre, z.y, acc.y);
+            acc.x = fma(-pr.kim, z.y, acc.x);
+            acc.y = fma(pr.kim, z.x, acc.y);
         }
         y[i] = acc;
     }
@@ -93,6 +109,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
     cplx* vk = reinterpret_cast<cplx*>(smem_raw);       // V_k
     cplx* vkm1 = vk + a.n;                              // V_{k-1}
     cplx* w = vkm1 + a.n;                               // H V_k, then W_k
+    FusedProd* sp = reinterpret_cast<FusedProd*>(w + a.n);   // [nprod]
     __shared__ double red[FUSED_THREADS / 32];
     __shared__ double2 s_alpha[MAX_ORDER_SMEM];
     __shared__ double s_beta[MAX_ORDER_SMEM + 1];
@@ -109,6 +126,23 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         vk[i] = v;
         a.slabs[0][s * n + i] = v;
     }
+    for (int p = threadIdx.x; p < a.nprod; p += FUSED_THREADS) {
+        const ProdD pr = a.prods[p];
+        FusedProd f;
+        f.ket_off = (int)pr.ket_off;
+        f.ent_off = (int)pr.ent_off;
+        f.nnz = __popc(a.tab_mask[pr.tab]);
+        f.pad = 0;
+        if (a.k_complex) {
+            const cplx kv = reinterpret_cast<const cplx*>(a.kpool)[pr.koff];
+            f.kre = kv.x;
+            f.kim = kv.y;
+        } else {
+            f.kre = a.kpool[pr.koff];
+            f.kim = 0.0;
+        }
+        sp[p] = f;
+    }
     if (threadIdx.x == 0) { s_c[0] = make_double2(1.0, 0.0); s_beta[0] = 0.0; }
     __syncthreads();
 
@@ -116,7 +150,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
     bool hit_max = (a.maxorder <= 1);
     for (;; ++k) {
         // w = H V_k ; alpha_k = vdot(w, V_k)
-        fused_matvec(a, vk, w);
+        fused_matvec(a, sp, vk, w);
         __syncthreads();
         double re = 0, im = 0;
         for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
