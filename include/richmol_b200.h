@@ -124,6 +124,16 @@ int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, dou
                                 double tol, int32_t maxorder, const double* h0phase_host,
                                 int32_t skip_krylov, int32_t* orders_host, void* stream);
 
+/* Same as rmb_propagate_step_host, and additionally evaluates <psi_s|O_o|psi_s> of the PROPAGATED states for
+ * `nobs` operators on the device before the download (expval_host: [nobs][nstates] complex) -- what the
+ * reference's examples do on the host after every update (examples/ocs_alignment.py:96-100), without a
+ * second upload.  The ensemble is processed in chunks so that uploads, kernels and downloads overlap.     */
+int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
+                                    int64_t nstates, int64_t ld, double fac_re, double fac_im,
+                                    double tol, int32_t maxorder, const double* h0phase_host,
+                                    int32_t skip_krylov, int32_t* orders_host, int32_t nobs,
+                                    rmb_operator** obs, double* expval_host, void* stream);
+
 /* K5 -- observables (user code in examples/ocs_alignment.py:99-100, tests/test_tdse.py:66).
  * expval_dev[s] = <psi_s| O |psi_s>  (complex, [nstates]), O given as an operator whose field has
  * been applied (rank-0 tensors: fprod = {1}).                                                       */

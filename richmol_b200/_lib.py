@@ -53,6 +53,10 @@ SYMBOLS = {
     "rmb_propagate_step_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                             C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p,
                                             C.c_int32, C.c_void_p, C.c_void_p]),
+    "rmb_propagate_step_host_obs": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                                C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p,
+                                                C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p),
+                                                C.c_void_p, C.c_void_p]),
     "rmb_expectation": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rmb_populations": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rmb_set_workspace_budget": (C.c_int32, [C.c_void_p, C.c_int64]),

@@ -98,6 +98,10 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_ctrl);
     if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
     cudaFree(op->d_stage);
+    cudaFree(op->d_expv);
+    if (op->s_in) cudaStreamDestroy(op->s_in);
+    if (op->s_out) cudaStreamDestroy(op->s_out);
+    for (auto e : op->pipe_events) cudaEventDestroy(e);
     cudaFree(op->d_phase);
     for (auto& e : op->mv_events) {
         cudaEventDestroy(e.first);
@@ -917,7 +921,8 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
     }
     // sub-batch size from the workspace budget: the product vector and ~15 Krylov vectors per state
     long long bc = op->ws_states;
-    if (bc < std::min<long long>(nstates, 65535) && !(op->ws_states > 0 && op->ws_budget_fixed)) {
+    if (bc < std::min<long long>(nstates, 65535)) {
+        // more states than the workspace holds: (re)size it from the budget (rare: first call / larger batch)
         long long budget = op->ws_budget;
         if (budget <= 0) {
             size_t fr = 0, tot = 0;
@@ -926,9 +931,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
             budget = (long long)(0.4 * (double)(fr + (size_t)held));
         }
         const long long per_state = 16LL * op->np * (long long)sizeof(cplx);
-        bc = std::max(1LL, std::min({(long long)nstates, budget / per_state, 65535LL}));
-        if (bc <= op->ws_states) bc = op->ws_states;
-        op->ws_budget_fixed = true;   // the size is settled for this handle unless the budget is changed
+        bc = std::max({1LL, op->ws_states, std::min({(long long)nstates, budget / per_state, 65535LL})});
     }
     bc = std::max(1LL, std::min(bc, (long long)nstates));
     if ((rc = ensure_workspace(op, bc, maxorder))) return rc;
@@ -1001,39 +1004,101 @@ int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, i
                             (const cplx*)h0phase_dev, skip_krylov, orders_host, (cudaStream_t)stream);
 }
 
-int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
-                                int64_t nstates, int64_t ld, double fac_re, double fac_im, double tol,
-                                int32_t maxorder, const double* h0phase_host, int32_t skip_krylov,
-                                int32_t* orders_host, void* stream) {
-    if (!op || !psi_in_host || !psi_out_host || ld < op->n || nstates < 0) {
+int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
+                                    int64_t nstates, int64_t ld, double fac_re, double fac_im, double tol,
+                                    int32_t maxorder, const double* h0phase_host, int32_t skip_krylov,
+                                    int32_t* orders_host, int32_t nobs, rmb_operator** obs,
+                                    double* expval_host, void* stream) {
+    if (!op || !psi_in_host || !psi_out_host || ld < op->n || nstates < 0 || nobs < 0 ||
+        (nobs > 0 && (!obs || !expval_host))) {
         set_error("propagate_step_host: bad arguments");
         return RMB_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long long elems = (long long)nstates * ld;
+    if (nstates == 0) return RMB_OK;
+    int rc;
     if (elems > op->stage_elems) {
         RMB_CUDA(cudaStreamSynchronize(st));
-        int rc = ensure(&op->d_stage, (size_t)elems);
-        if (rc) return rc;
+        if ((rc = ensure(&op->d_stage, (size_t)elems))) return rc;
         op->stage_elems = elems;
+    }
+    if ((long long)nobs * nstates > op->expv_elems) {
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if ((rc = ensure(&op->d_expv, (size_t)nobs * nstates))) return rc;
+        op->expv_elems = (long long)nobs * nstates;
+    }
+    if (!op->s_in) {
+        RMB_CUDA(cudaStreamCreateWithFlags(&op->s_in, cudaStreamNonBlocking));
+        RMB_CUDA(cudaStreamCreateWithFlags(&op->s_out, cudaStreamNonBlocking));
     }
     const cplx* ph = nullptr;
     if (h0phase_host) {
         if (op->n > op->phase_elems) {
-            int rc = ensure(&op->d_phase, (size_t)op->n);
-            if (rc) return rc;
+            if ((rc = ensure(&op->d_phase, (size_t)op->n))) return rc;
             op->phase_elems = op->n;
         }
         RMB_CUDA(cudaMemcpyAsync(op->d_phase, h0phase_host, sizeof(cplx) * op->n, cudaMemcpyHostToDevice, st));
         ph = op->d_phase;
     }
-    RMB_CUDA(cudaMemcpyAsync(op->d_stage, psi_in_host, sizeof(cplx) * elems, cudaMemcpyHostToDevice, st));
-    int rc = propagate_device(op, op->d_stage, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder, ph,
-                              skip_krylov, orders_host, st);
-    if (rc != RMB_OK && rc != RMB_ERR_MAXORDER) return rc;
-    RMB_CUDA(cudaMemcpyAsync(psi_out_host, op->d_stage, sizeof(cplx) * elems, cudaMemcpyDeviceToHost, st));
+    // Chunked pipeline: upload of chunk c+1 and download of chunk c-1 overlap the propagation of chunk c
+    // (PCIe is full duplex; uploads on s_in, downloads on s_out, kernels on the caller's stream).
+    int want = 3;
+    if (const char* e = getenv("RMB_HOST_CHUNKS")) want = std::max(1, atoi(e));
+    long long cs = nstates >= 128 ? (nstates + want - 1) / want : nstates;
+    cs = std::max<long long>(2, (cs + 1) & ~1LL);
+    const int nchunk = (int)((nstates + cs - 1) / cs);
+    while ((int)op->pipe_events.size() < 2 * nchunk + 1) {
+        cudaEvent_t e;
+        RMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        op->pipe_events.push_back(e);
+    }
+    // uploads must not overtake the previous call's downloads of the same staging buffer
+    RMB_CUDA(cudaEventRecord(op->pipe_events[2 * nchunk], st));
+    RMB_CUDA(cudaStreamWaitEvent(op->s_in, op->pipe_events[2 * nchunk], 0));
+    for (int c = 0; c < nchunk; ++c) {
+        const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
+        RMB_CUDA(cudaMemcpyAsync(op->d_stage + c0 * ld, (const cplx*)psi_in_host + c0 * ld, sizeof(cplx) * b * ld,
+                                 cudaMemcpyHostToDevice, op->s_in));
+        RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c], op->s_in));
+    }
+    int result = RMB_OK;
+    for (int c = 0; c < nchunk; ++c) {
+        const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
+        RMB_CUDA(cudaStreamWaitEvent(st, op->pipe_events[2 * c], 0));
+        rc = propagate_device(op, op->d_stage + c0 * ld, b, ld, make_double2(fac_re, fac_im), tol, maxorder, ph,
+                              skip_krylov, orders_host ? orders_host + c0 : nullptr, st);
+        if (rc == RMB_ERR_MAXORDER) result = rc;
+        else if (rc != RMB_OK) return rc;
+        for (int o = 0; o < nobs; ++o) {
+            rc = rmb_expectation(obs[o], (const double*)(op->d_stage + c0 * ld), b, ld,
+                                 (double*)(op->d_expv + (long long)o * nstates + c0), st);
+            if (rc != RMB_OK) return rc;
+        }
+        RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c + 1], st));
+        RMB_CUDA(cudaStreamWaitEvent(op->s_out, op->pipe_events[2 * c + 1], 0));
+        RMB_CUDA(cudaMemcpyAsync((cplx*)psi_out_host + c0 * ld, op->d_stage + c0 * ld, sizeof(cplx) * b * ld,
+                                 cudaMemcpyDeviceToHost, op->s_out));
+    }
+    if (nobs > 0)
+        RMB_CUDA(cudaMemcpyAsync(expval_host, op->d_expv, sizeof(cplx) * (size_t)nobs * nstates,
+                                 cudaMemcpyDeviceToHost, st));
     RMB_CUDA(cudaStreamSynchronize(st));
-    return rc;
+    RMB_CUDA(cudaStreamSynchronize(op->s_out));
+    if (result == RMB_ERR_MAXORDER) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
+        set_error(buf);
+    }
+    return result;
+}
+
+int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
+                                int64_t nstates, int64_t ld, double fac_re, double fac_im, double tol,
+                                int32_t maxorder, const double* h0phase_host, int32_t skip_krylov,
+                                int32_t* orders_host, void* stream) {
+    return rmb_propagate_step_host_obs(op, psi_in_host, psi_out_host, nstates, ld, fac_re, fac_im, tol, maxorder,
+                                       h0phase_host, skip_krylov, orders_host, 0, nullptr, nullptr, stream);
 }
 
 int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates, int64_t ld,
@@ -1093,7 +1158,6 @@ int32_t rmb_populations(const double* psi_dev, int64_t nstates, int64_t n, int64
 int32_t rmb_set_workspace_budget(rmb_operator* op, int64_t bytes) {
     if (!op) return RMB_ERR_INVALID;
     op->ws_budget = bytes;
-    op->ws_budget_fixed = false;
     return RMB_OK;
 }
 

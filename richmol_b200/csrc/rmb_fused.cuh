@@ -105,7 +105,7 @@ __device__ __forceinline__ void fused_matvec(const FusedArgs& a, const FusedProd
 
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 k_lanczos_fused(const FusedArgs a, long long nstates) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* vk = reinterpret_cast<cplx*>(smem_raw);       // V_k
     cplx* vkm1 = vk + a.n;                              // V_{k-1}
     cplx* w = vkm1 + a.n;                               // H V_k, then W_k

@@ -133,7 +133,6 @@ struct rmb_operator {
     rmb::cplx* d_dc = nullptr;       // [S][maxorder] (c^k - c^{k-1}) * rinv
     rmb::cplx* d_ceff = nullptr;     // [S][maxorder] c^k * rinv
     double* d_rinv = nullptr;        // [S][maxorder+1] 1/beta_k (1 for k = 0 and after a fallback)
-    bool ws_budget_fixed = false;
     std::vector<cudaEvent_t> it_events;
     int* d_active = nullptr;         // [S]
     int* d_order = nullptr;          // [S]
@@ -146,6 +145,10 @@ struct rmb_operator {
     // host staging for the *_host entry point
     rmb::cplx* d_stage = nullptr;
     long long stage_elems = 0;
+    rmb::cplx* d_expv = nullptr;     // [nobs][nstates] expectation values of the host entry point
+    long long expv_elems = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // upload / download streams of the chunked pipeline
+    std::vector<cudaEvent_t> pipe_events;
     rmb::cplx* d_phase = nullptr;
     long long phase_elems = 0;
 

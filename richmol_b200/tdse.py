@@ -222,7 +222,9 @@ class TDSE():
         Kwargs: `H0` (field-free Hamiltonian -> split-operator step), `matvec_lib` (accepted,
         ignored: the CUDA path is the only one), `propag` ('internal'; 'external' is served by the
         same Lanczos kernel), `tol` (default 1e-15), and the extensions
-        `inplace` (CUDA tensors only) and `out` (numpy result buffer, e.g. pinned memory)."""
+        `inplace` (CUDA tensors only), `out` (numpy result buffer, e.g. pinned memory) and `expect`
+        (numpy path: list of observables whose per-state expectation values of the propagated states are
+        left in `tdse.last_expect[(iobs, istate)]`, computed on the device before the download)."""
         import ctypes as C
 
         if 'H0' in kwargs:
@@ -323,11 +325,19 @@ class TDSE():
             raise ValueError("`out` must be a C-contiguous complex128 array of the shape of `vecs`")
         orders = np.zeros(nst, dtype=np.int32)
         ph = np.ascontiguousarray(phase, dtype=np.complex128) if phase is not None else None
-        status = lib.rmb_propagate_step_host(
+        # extension: observables of the propagated states evaluated on the device before the download
+        obs = [_as_cartens(O, {}) for O in kwargs.get('expect', ())]
+        for O in obs:
+            if not O._has_field() and getattr(O, "cart", [None])[0] == "0":
+                O.field([0, 0, 1])
+        handles = (C.c_void_p * max(1, len(obs)))(*[O._device(stream).handle for O in obs])
+        expv = np.zeros((len(obs), nst), dtype=np.complex128)
+        status = lib.rmb_propagate_step_host_obs(
             op.handle, vin.ctypes.data, vout.ctypes.data, nst, N, exp_fac.real, exp_fac.imag,
             float(tol), 100, ph.ctypes.data if ph is not None else None, int(skip),
-            orders.ctypes.data, stream)
+            orders.ctypes.data, len(obs), handles, expv.ctypes.data, stream)
         self._orders = orders
+        self.last_expect = expv
         _lib.check(status)
         return vout
 
