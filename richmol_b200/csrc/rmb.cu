@@ -11,6 +11,7 @@
 #include "rmb_kernels.cuh"
 #include "rmb_matvec.cuh"
 #include "rmb_fused.cuh"
+#include "rmb_matvec_gemm.cuh"
 
 namespace rmb {
 
@@ -64,6 +65,8 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_blk_off);
     cudaFree(op->d_blk_dm);
     cudaFree(op->d_items2);
+    cudaFree(op->d_itemsG);
+    cudaFree(op->d_unitsG);
     cudaFree(op->d_gdesc);
     cudaFree(op->d_ktpool);
     cudaFree(op->d_units);
@@ -278,8 +281,14 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (2 * MV2_STAGES + 1) * 8 + (size_t)nprod * 4 + 128;
     };
     const char* force = getenv("RMB_MATVEC");
+    auto itemG_smem = [](size_t xbuf_elems, int nrows, int ldk) {
+        return xbuf_elems * 16 + (size_t)MV2_NDMAX * nrows * sizeof(MfEntry) + (size_t)2 * MG_M * MG_LDZ * 8 +
+               (size_t)MG_KCH * ldk * 8 + 64 + 128;
+    };
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
+    std::vector<ItemG> itemsG;
+    const bool force_nogemm = force && strcmp(force, "nogemm") == 0;
     std::vector<XRange> xranges;
     std::vector<ProdS> gdesc;                 // static per-(item, product) descriptors, shared-memory layout
     std::vector<double> ktpool;               // K^T images per (bra block, column chunk), shared-memory layout
@@ -296,6 +305,100 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             // algorithmic work: K contraction + banded M contraction
             flops += (kc ? 8.0 : 4.0) * dm1 * (double)dk1 * pr.dk2 + 8.0 * (double)pr.nd * dm1 * pr.dk2;
             opbytes += (kc ? 16.0 : 8.0) * dk1 * pr.dk2;
+        }
+        // ---- DMMA kernel for wide real K blocks: all columns (<= 64 per item) in registers, Z staged once
+        if (!force_scalar && !force_nogemm && !kc && dk1 > MV2_NCMAX && ndmax <= MV2_NDMAX) {
+            // rows per tile: nst * nrows <= MG_M, ket rows of all states of the tile must fit the buffer
+            int best_nt = 0, best_nst = 0;
+            double best_util = -1;
+            const int nt0 = (dm1 + MG_M - 1) / MG_M;
+            for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
+                const int nr = (dm1 + nt - 1) / nt;
+                int nst = std::max(1, MG_M / nr);
+                auto need = [&](int nst_) {
+                    size_t xb = 256;
+                    for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
+                        const ProdD& q = op->h_prods[p];
+                        xb = std::max(xb, (size_t)nst_ * std::min(q.dm2, nr + h_span[p]) * (q.dk2 | 1));
+                    }
+                    const int ncm = std::min(dk1, 8 * MG_NTMAX);
+                    const int ldk = ((ncm + 7) / 8) * 8 + 4 + ((((ncm + 7) / 8) * 8 + 4) % 16 == 4 ? 0 : 8);
+                    return itemG_smem((xb + 1) & ~(size_t)1, nr, ldk);
+                };
+                while (nst > 1 && need(nst) > smem_budget) --nst;
+                if (need(nst) > smem_budget) continue;
+                const double util = (double)nr * nst / MG_M * ((double)dm1 / (nr * nt));
+                if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_nst = nst; }
+            }
+            if (best_nt > 0) {
+                const int nr_t = (dm1 + best_nt - 1) / best_nt;
+                for (int c0 = 0; c0 < dk1; c0 += 8 * MG_NTMAX)
+                    for (int r0 = 0; r0 < dm1; r0 += nr_t) {
+                        ItemG it;
+                        it.bra_off = poff[b];
+                        it.dk1 = dk1;
+                        it.dm1 = dm1;
+                        it.r0 = r0;
+                        it.nrows = std::min(nr_t, dm1 - r0);
+                        it.c0 = c0;
+                        it.nc = std::min(8 * MG_NTMAX, dk1 - c0);
+                        it.nt = (it.nc + 7) / 8;
+                        it.ldk = it.nt * 8 + 4;
+                        if (it.ldk % 16 != 4) it.ldk += 8;            // == 4 (mod 16): conflict-free B fragments
+                        it.p_begin = bra_begin[b];
+                        it.p_end = bra_begin[b + 1];
+                        it.nst = best_nst;
+                        it.desc_off = (int)gdesc.size();
+                        it.pad = 0;
+                        int xbe = 256;
+                        for (int p = it.p_begin; p < it.p_end; ++p) {
+                            const ProdD& q = op->h_prods[p];
+                            int lo = q.dm2, hi = -1;
+                            for (int r = it.r0; r < it.r0 + it.nrows; ++r)
+                                for (int j = 0; j < q.nd; ++j) {
+                                    const int col = ent_col[q.ent_off + (long long)r * q.nd + j];
+                                    if (col >= 0) { lo = std::min(lo, col); hi = std::max(hi, col); }
+                                }
+                            ProdS ds;
+                            ds.c_lo = hi < 0 ? 0 : lo;
+                            ds.nr = hi < 0 ? 0 : hi - lo + 1;
+                            ds.ket_off = q.ket_off + (long long)ds.c_lo * (q.dk2 | 1);
+                            ds.ent_off = q.ent_off;
+                            ds.dk2 = q.dk2;
+                            ds.nnz = 0;
+                            ds.xrs = q.dk2 | 1;
+                            ds.tab = q.tab;
+                            ds.pad1 = ds.pad2 = 0;
+                            gdesc.push_back(ds);
+                            xbe = std::max(xbe, it.nst * ds.nr * (q.dk2 | 1));
+                        }
+                        it.xbuf_elems = (xbe + 1) & ~1;
+                        // K^T images [dk2 padded to MG_KCH][ldk] per product, zero padded, shared by the row
+                        // tiles of this (bra block, column tile)
+                        auto key = std::make_pair(-1 - b, c0);
+                        auto found = kt_index.find(key);
+                        if (found == kt_index.end()) {
+                            while (ktpool.size() % 2) ktpool.push_back(0.0);
+                            const long long off = (long long)ktpool.size();
+                            kt_index[key] = off;
+                            for (int p = it.p_begin; p < it.p_end; ++p) {
+                                const ProdD& q = op->h_prods[p];
+                                const int k2p = ((q.dk2 + MG_KCH - 1) / MG_KCH) * MG_KCH;
+                                for (int k2 = 0; k2 < k2p; ++k2)
+                                    for (int c = 0; c < it.ldk; ++c)
+                                        ktpool.push_back((k2 < q.dk2 && c < it.nc)
+                                                             ? kpool[(size_t)(q.koff + (long long)(c0 + c) * q.dk2 + k2)]
+                                                             : 0.0);
+                            }
+                            it.kt_off = off;
+                        } else {
+                            it.kt_off = found->second;
+                        }
+                        op->matvecG_smem = std::max(op->matvecG_smem, itemG_smem((size_t)it.xbuf_elems, it.nrows, it.ldk));
+                        itemsG.push_back(it);
+                    }
+                continue;
+            }
         }
         // ---- tiled kernel: row tiles (<= 128 rows, one thread per row and state pair) x column
         //      chunks (<= 16); falls back to the scalar kernel when the tile does not fit
@@ -441,6 +544,16 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         for (int i : order) sorted.push_back(items2[i]);
         items2.swap(sorted);
     }
+    {
+        auto costG = [&](const ItemG& it) {
+            double c = 0;
+            for (int p = it.p_begin; p < it.p_end; ++p) c += (double)it.nrows * it.nst * op->h_prods[p].dk2 * it.nc;
+            return c;
+        };
+        std::stable_sort(itemsG.begin(), itemsG.end(), [&](const ItemG& a, const ItemG& b) { return costG(a) > costG(b); });
+    }
+    op->nitemsG = (int)itemsG.size();
+    for (auto& it : itemsG) op->h_itemG_states.push_back(it.nst);
     op->nitems2 = (int)items2.size();
     for (auto& it : items2) op->h_item2_states.push_back(it.nst);
 
@@ -486,6 +599,14 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             }
             const char* ff = getenv("RMB_FUSED");
             op->fused_ok = !(ff && strcmp(ff, "0") == 0);
+        }
+    }
+    if ((rc = upload((ItemG**)&op->d_itemsG, itemsG.data(), itemsG.size()))) return rc;
+    {
+        static size_t g_gemm_smem = 16 * 1024;
+        if (op->matvecG_smem > g_gemm_smem) {
+            RMB_CUDA(cudaFuncSetAttribute(k_matvec_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->matvecG_smem));
+            g_gemm_smem = op->matvecG_smem;
         }
     }
     if ((rc = upload((ProdS**)&op->d_gdesc, gdesc.data(), gdesc.size()))) return rc;
@@ -621,7 +742,7 @@ struct MvEpilogue {
 
 static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
                          long long ldy, const int* active, cudaStream_t st, const MvEpilogue& ep = MvEpilogue()) {
-    if ((op->nitems == 0 && op->nitems2 == 0) || nstates == 0) return RMB_OK;
+    if ((op->nitems == 0 && op->nitems2 == 0 && op->nitemsG == 0) || nstates == 0) return RMB_OK;
     const int S = op->matvec_S;
     const int zstride = (int)(op->matvec_smem / (S * sizeof(cplx)));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -665,6 +786,29 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
                 ep.scale, ep.scale_stride, ep.pdot, ep.npart);
         op->n_launches++;
     }
+    if (op->nitemsG > 0) {
+        if (op->unitsG_nstates != nstates) {
+            std::vector<Unit2D> units;
+            for (int i = 0; i < op->nitemsG; ++i)
+                for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0});
+            if ((int)units.size() > op->unitsG_cap) {
+                RMB_CUDA(cudaStreamSynchronize(st));
+                if (op->d_unitsG) cudaFree(op->d_unitsG);
+                op->unitsG_cap = (int)units.size();
+                RMB_CUDA(cudaMalloc(&op->d_unitsG, sizeof(Unit2D) * op->unitsG_cap));
+            }
+            RMB_CUDA(cudaMemcpyAsync(op->d_unitsG, units.data(), sizeof(Unit2D) * units.size(),
+                                     cudaMemcpyHostToDevice, st));
+            RMB_CUDA(cudaStreamSynchronize(st));
+            op->nunitsG = (int)units.size();
+            op->unitsG_nstates = nstates;
+        }
+        k_matvec_gemm<<<op->nunitsG, MG_THREADS, op->matvecG_smem, st>>>(
+            (const Unit2D*)op->d_unitsG, (const ItemG*)op->d_itemsG, (const ProdS*)op->d_gdesc,
+            (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_ktpool, X, Y, ldx, ldy, (int)nstates, active,
+            ep.scale, ep.scale_stride, ep.pdot, ep.npart, op->nitems2);
+        op->n_launches++;
+    }
     // scalar kernel for the bra blocks the tiled kernel does not cover (no fused epilogue: callers
     // check op->nitems == 0 before asking for one); grid.y is limited to 65535
     const long long max_y = 65535;
@@ -699,8 +843,8 @@ static int ensure(T** p, size_t count) {
 }
 
 // the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
-static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 > 0; }
-static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 : op->nchunk; }
+static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 + op->nitemsG > 0; }
+static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 + op->nitemsG : op->nchunk; }
 
 // (re)allocate the per-state small arrays and the product vector for `cap` states
 static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
@@ -714,7 +858,7 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     op->nchunk = nchunks(op->np);
     int rc;
     const size_t vec = (size_t)cap * (size_t)op->np;
-    const size_t np = (size_t)std::max(op->nchunk, op->nitems2);
+    const size_t np = (size_t)std::max(op->nchunk, op->nitems2 + op->nitemsG);
     if ((rc = ensure(&op->d_w, vec))) return rc;
     RMB_CUDA(cudaMemset(op->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
     if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
@@ -1126,9 +1270,9 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
             // the product vector itself is never written
             MvEpilogue ep;
             ep.pdot = op->d_pdot;
-            ep.npart = op->nitems2;
+            ep.npart = dot_parts(op);
             if ((rc = launch_matvec(op, op->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
-            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, op->nitems2, (cplx*)expval_dev + s0, -1.0);
+            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;
         } else {
             if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st))) return rc;

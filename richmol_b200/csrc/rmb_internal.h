@@ -101,6 +101,14 @@ struct rmb_operator {
     int nunits = 0;
     int units_cap = 0;
     std::vector<int> h_item2_states; // states per CTA of each tiled item
+    // DMMA matvec for wide K blocks (rmb_matvec_gemm.cuh)
+    int nitemsG = 0;
+    void* d_itemsG = nullptr;        // ItemG[]
+    void* d_unitsG = nullptr;
+    int nunitsG = 0, unitsG_cap = 0;
+    long long unitsG_nstates = -1;
+    std::vector<int> h_itemG_states;
+    size_t matvecG_smem = 0;
     int kt_doubles = 0;
     int xbuf_elems = 0;
     int np_max = 0;

@@ -494,3 +494,23 @@ def test_host_pipeline_with_device_side_observables():
     cm = oc.tomat()
     ref = np.array([np.vdot(v, cm.dot(v)) for v in out_host[:5]])
     assert relerr(t1.last_expect[0][:5], ref) < TOL
+
+
+def test_wide_k_blocks_dmma_path_propagation():
+    """dim_k ~ 20 and dim_m = 81/83: the DMMA kernel (Z staged once, mma.sync m8n8k4 f64) with several
+    row tiles per bra block, inside a full split-operator Lanczos step (fused <w,V_k> epilogue)."""
+    st = synth.asymmetric_rotor(*synth.H2S_ABC, 41, Jmin=40)
+    h0 = synth.hamiltonian_tensor(st)
+    pol = synth.lab_tensor(synth.H2S_POL, st) * (-0.5 * AUPOL)
+    N = pol._basis().N
+    assert max(pol._basis().dk) >= 20
+    opol = oracle_of(pol)
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    vecs0 = random_states(5, N, seed=21)
+    E = [3e9, -2e9, 4e9]
+    pol.field(E)
+    opol.field(E)
+    x = random_states(3, N, seed=22)
+    assert relerr(gpu_matvec(pol, x), np.array([port.flat_matvec(opol, xi) for xi in x])) < 1e-13
+    _run_both(h0, lambda E_: pol, lambda E_: opol, [E], vecs0, tdse)
