@@ -282,13 +282,15 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     };
     const char* force = getenv("RMB_MATVEC");
     auto itemG_smem = [](size_t xbuf_elems, int nrows, int ldk) {
-        return xbuf_elems * 16 + (size_t)MV2_NDMAX * nrows * sizeof(MfEntry) + (size_t)2 * MG_M * MG_LDZ * 8 +
-               (size_t)MG_KCH * ldk * 8 + 64 + 128;
+        return xbuf_elems * 16 + (size_t)MV2_NDMAX * nrows * sizeof(MfEntry) + (size_t)4 * MG_M * MG_LDZ * 8 +
+               (size_t)2 * MG_KCH * ldk * 8 + 64 + 128;
     };
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
     std::vector<ItemG> itemsG;
     const bool force_nogemm = force && strcmp(force, "nogemm") == 0;
+    int gemm_min_dk = MV2_NCMAX;              // bra blocks with more columns go to the DMMA kernel
+    if (const char* e = getenv("RMB_GEMM_MIN_DK")) gemm_min_dk = atoi(e);
     std::vector<XRange> xranges;
     std::vector<ProdS> gdesc;                 // static per-(item, product) descriptors, shared-memory layout
     std::vector<double> ktpool;               // K^T images per (bra block, column chunk), shared-memory layout
@@ -307,7 +309,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             opbytes += (kc ? 16.0 : 8.0) * dk1 * pr.dk2;
         }
         // ---- DMMA kernel for wide real K blocks: all columns (<= 64 per item) in registers, Z staged once
-        if (!force_scalar && !force_nogemm && !kc && dk1 > MV2_NCMAX && ndmax <= MV2_NDMAX) {
+        if (!force_scalar && !force_nogemm && !kc && dk1 > gemm_min_dk && ndmax <= MV2_NDMAX) {
             // rows per tile: nst * nrows <= MG_M, ket rows of all states of the tile must fit the buffer
             int best_nt = 0, best_nst = 0;
             double best_util = -1;

@@ -53,10 +53,9 @@ __device__ __forceinline__ void mg_body(const ItemG& it, const ProdS* __restrict
     // ---- shared memory carve-up
     double2* xbuf = reinterpret_cast<double2*>(smem_raw);
     MfEntry* mfe = reinterpret_cast<MfEntry*>(xbuf + it.xbuf_elems);
-    double* zre = reinterpret_cast<double*>(mfe + MV2_NDMAX * it.nrows);
-    double* zim = zre + MG_M * MG_LDZ;
-    double* ktc = zim + MG_M * MG_LDZ;                                   // [MG_KCH][ldk]
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(ktc + MG_KCH * it.ldk);
+    double* zbuf = reinterpret_cast<double*>(mfe + MV2_NDMAX * it.nrows);  // [2][re|im][MG_M][MG_LDZ]
+    double* kbuf = zbuf + 4 * MG_M * MG_LDZ;                               // [2][MG_KCH][ldk]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(kbuf + 2 * MG_KCH * it.ldk);
     __shared__ int s_nnz;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,10 +78,9 @@ __device__ __forceinline__ void mg_body(const ItemG& it, const ProdS* __restrict
 #pragma unroll
     for (int n = 0; n < NT; ++n) cre[n][0] = cre[n][1] = cim[n][0] = cim[n][1] = 0.0;
 
-    // rows handled by this thread in the Z build: row = tid / 4, four consecutive k2 per thread
-    const int zrow = threadIdx.x >> 2, zk = (threadIdx.x & 3) * 4;
-    const int zs = zrow / it.nrows, zm = zrow - zs * it.nrows;
-    const bool zvalid = zrow < mrows;
+    // Z build: a quarter warp (8 lanes) reads 8 consecutive k2 of ONE row (128 contiguous bytes: no bank
+    // conflicts); each thread handles rows zrow0 and zrow0 + 32 and k2 offsets zk and zk + 8
+    const int zrow0 = threadIdx.x >> 3, zk = threadIdx.x & 7;
 
     long long ktoff = it.kt_off;
     unsigned phase = 0;
@@ -113,59 +111,76 @@ __device__ __forceinline__ void mg_body(const ItemG& it, const ProdS* __restrict
         const int nnz = s_nnz;
         mbar_wait(bar, phase);
         phase ^= 1u;
-        // MF row of this thread's Z row
-        double2 mf[MV2_NDMAX];
-        int xo[MV2_NDMAX];
+        // MF rows of this thread's two Z rows
+        double2 mf[2][MV2_NDMAX];
+        int xo[2][MV2_NDMAX];
+        const double2* xs[2];
+        bool zvalid[2];
 #pragma unroll
-        for (int q = 0; q < MV2_NDMAX; ++q) {
-            mf[q] = make_double2(0.0, 0.0);
-            xo[q] = 0;
-            if (q < nnz && zvalid) {
-                const MfEntry e = mfe[q * it.nrows + zm];
-                if (e.col >= 0) {
-                    mf[q] = make_double2(e.re, e.im);
-                    xo[q] = (e.col - d.c_lo) * d.xrs;
+        for (int h = 0; h < 2; ++h) {
+            const int zrow = zrow0 + 32 * h;
+            const int zs = zrow / it.nrows, zm = zrow - zs * it.nrows;
+            zvalid[h] = zrow < mrows;
+            xs[h] = xbuf + (long long)zs * d.nr * d.xrs;
+#pragma unroll
+            for (int q = 0; q < MV2_NDMAX; ++q) {
+                mf[h][q] = make_double2(0.0, 0.0);
+                xo[h][q] = 0;
+                if (q < nnz && zvalid[h]) {
+                    const MfEntry e = mfe[q * it.nrows + zm];
+                    if (e.col >= 0) {
+                        mf[h][q] = make_double2(e.re, e.im);
+                        xo[h][q] = (e.col - d.c_lo) * d.xrs;
+                    }
                 }
             }
         }
-        const double2* xs = xbuf + (long long)zs * d.nr * d.xrs;
-        // ---- k2 chunks: K^T chunk -> smem, Z chunk -> smem, DMMA (skipped when the field left no diagonal)
-        for (int k0 = 0; nnz > 0 && k0 < d.dk2; k0 += MG_KCH) {
-            if (k0 > 0) __syncthreads();                   // previous chunk's fragments consumed
-            // K^T chunk (host image: [dk2 padded to 16][ldk], zero padded)
-            {
-                const double* src = ktpool + ktoff + (long long)k0 * it.ldk;
-                const int n = MG_KCH * it.ldk;
-                for (int i = threadIdx.x * 2; i < n; i += MG_THREADS * 2)
-                    *reinterpret_cast<double2*>(ktc + i) = *reinterpret_cast<const double2*>(src + i);
-            }
-            // Z chunk: zre/zim[row][k2 - k0]
-            {
+        const int nchunks = nnz > 0 ? (d.dk2 + MG_KCH - 1) / MG_KCH : 0;
+        // stage chunk c: K^T chunk by cp.async (host image [dk2 padded to 16][ldk]), Z chunk by FMA
+        auto stage_chunk = [&](int c) {
+            double* kc_ = kbuf + (c & 1) * MG_KCH * it.ldk;
+            const double* src = ktpool + ktoff + (long long)c * MG_KCH * it.ldk;
+            const int n16 = MG_KCH * it.ldk / 2;                 // 16-byte pieces
+            for (int i = threadIdx.x; i < n16; i += MG_THREADS)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(kc_ + 2 * i)), "l"(src + 2 * i));
+            asm volatile("cp.async.commit_group;\n" ::);
+            double* zr = zbuf + (c & 1) * 2 * MG_M * MG_LDZ;
+            double* zi = zr + MG_M * MG_LDZ;
+            const int k0 = c * MG_KCH;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k2 = k0 + zk + j;
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k2 = k0 + zk + 8 * j;
                     double2 z = make_double2(0.0, 0.0);
-                    if (zvalid && k2 < d.dk2) {
+                    if (zvalid[h] && k2 < d.dk2) {
 #pragma unroll
                         for (int q = 0; q < MV2_NDMAX; ++q)
                             if (q < nnz) {
-                                const double2 a = xs[xo[q] + k2];
-                                z.x = fma(mf[q].x, a.x, z.x);
-                                z.y = fma(mf[q].x, a.y, z.y);
-                                z.x = fma(-mf[q].y, a.y, z.x);
-                                z.y = fma(mf[q].y, a.x, z.y);
+                                const double2 a = xs[h][xo[h][q] + k2];
+                                z.x = fma(mf[h][q].x, a.x, z.x);
+                                z.y = fma(mf[h][q].x, a.y, z.y);
+                                z.x = fma(-mf[h][q].y, a.y, z.x);
+                                z.y = fma(mf[h][q].y, a.x, z.y);
                             }
                     }
-                    zre[zrow * MG_LDZ + zk + j] = z.x;
-                    zim[zrow * MG_LDZ + zk + j] = z.y;
+                    zr[(zrow0 + 32 * h) * MG_LDZ + zk + 8 * j] = z.x;
+                    zi[(zrow0 + 32 * h) * MG_LDZ + zk + 8 * j] = z.y;
                 }
-            }
+        };
+        if (nchunks > 0) {
+            stage_chunk(0);
+            asm volatile("cp.async.wait_group 0;\n" ::);
             __syncthreads();
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            // overlap: stage chunk c+1 (other buffers) while the tensor pipe works on chunk c
+            if (c + 1 < nchunks) stage_chunk(c + 1);
             {
-                // ---- DMMA: C[8 rows of this warp][NT*8] += Z[8][16] K^T[16][NT*8]
-                const double* are = zre + (warp * 8 + (lane >> 2)) * MG_LDZ + (lane & 3);
-                const double* aim = zim + (warp * 8 + (lane >> 2)) * MG_LDZ + (lane & 3);
-                const double* bb = ktc + (lane & 3) * it.ldk + (lane >> 2);
+                const double* zr = zbuf + (c & 1) * 2 * MG_M * MG_LDZ;
+                const double* are = zr + (warp * 8 + (lane >> 2)) * MG_LDZ + (lane & 3);
+                const double* aim = are + MG_M * MG_LDZ;
+                const double* bb = kbuf + (c & 1) * MG_KCH * it.ldk + (lane & 3) * it.ldk + (lane >> 2);
 #pragma unroll
                 for (int kk = 0; kk < MG_KCH / 4; ++kk) {
                     const double ar = are[kk * 4], ai = aim[kk * 4];
@@ -177,6 +192,8 @@ __device__ __forceinline__ void mg_body(const ItemG& it, const ProdS* __restrict
                     }
                 }
             }
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            __syncthreads();       // chunk c consumed by every warp, chunk c+1 complete
         }
         ktoff += (long long)((d.dk2 + MG_KCH - 1) / MG_KCH) * MG_KCH * it.ldk;
     }
@@ -213,7 +230,7 @@ __device__ __forceinline__ void mg_body(const ItemG& it, const ProdS* __restrict
         pre += __shfl_xor_sync(0xffffffffu, pre, 2);
         pim += __shfl_xor_sync(0xffffffffu, pim, 2);
         __syncthreads();
-        double* red = zre;                                   // [2][MG_M]
+        double* red = zbuf;                                  // [2][MG_M]
         if ((lane & 3) == 0) {
             red[row] = valid ? pre : 0.0;
             red[MG_M + row] = valid ? pim : 0.0;
