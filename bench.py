@@ -452,7 +452,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="h2o", choices=["h2o", "ocs"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-states-per-core", type=int, default=2)
+    ap.add_argument("--cpu-states-per-core", type=int, default=4)
     args = ap.parse_args()
     NSTATES = NSTATES_BY_WORKLOAD[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -482,7 +482,7 @@ def main():
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (workers are spawned, not forked)
         m = build_model(args.workload)
-        v, cores, sample, _ = cpu_run(args.workload, m["h0"], 2, 1, args.cpu_states_per_core)
+        v, cores, sample, _ = cpu_run(args.workload, m["h0"], 6, 1, args.cpu_states_per_core)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = gpu_run(args)
     if line is not None:
