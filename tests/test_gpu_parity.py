@@ -514,3 +514,45 @@ def test_wide_k_blocks_dmma_path_propagation():
     x = random_states(3, N, seed=22)
     assert relerr(gpu_matvec(pol, x), np.array([port.flat_matvec(opol, xi) for xi in x])) < 1e-13
     _run_both(h0, lambda E_: pol, lambda E_: opol, [E], vecs0, tdse)
+
+
+def test_sub_batching_and_strided_states():
+    """A workspace budget smaller than the ensemble forces the sub-batch loop; a leading dimension larger
+    than N (rows of a wider array) must give the same states."""
+    import ctypes as C
+    import torch
+    from richmol_b200 import _lib
+    m = synth.h2o(5)
+    h0, pol = m["h0"], m["pol"] * (-0.5 * AUPOL)
+    pol.field([1e9, 0.0, 2e9])
+    N = pol._basis().N
+    vecs = random_states(45, N, seed=31)
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    ref, _ = tdse.update(pol, torch.from_numpy(vecs).cuda(), H0=h0)
+    ref_orders = tdse.last_orders.copy()
+    # fresh operator with a tiny budget: 7 states per sub-batch
+    from richmol_b200.field import clear_device_cache
+    clear_device_cache()
+    pol2 = synth.h2o(5)["pol"] * (-0.5 * AUPOL)
+    pol2.field([1e9, 0.0, 2e9])
+    op = pol2._device()
+    _lib.check(_lib.lib().rmb_set_workspace_budget(op.handle, C.c_int64(7 * 16 * 16 * int(op.basis.N * 1.2))))
+    t2 = TDSE(t_end=1, dt=0.01)
+    t2.time_grid()
+    out, _ = t2.update(pol2, torch.from_numpy(vecs).cuda(), H0=h0)
+    assert torch.equal(out, ref)
+    assert np.array_equal(t2.last_orders, ref_orders)
+    # strided rows through the C ABI directly
+    ld = N + 13
+    wide = torch.zeros((45, ld), dtype=torch.complex128, device="cuda")
+    wide[:, :N] = torch.from_numpy(vecs).cuda()
+    wide[:, N:] = 7.0
+    phase = torch.from_numpy(port.h0_phase(oracle_of(h0), EXP_FAC)).cuda()
+    orders = np.zeros(45, dtype=np.int32)
+    _lib.check(_lib.lib().rmb_propagate_step(op.handle, wide.data_ptr(), 45, ld, EXP_FAC.real, EXP_FAC.imag, 1e-15,
+                                             100, phase.data_ptr(), 0, orders.ctypes.data, None))
+    torch.cuda.synchronize()
+    assert torch.equal(wide[:, :N], ref)
+    assert bool((wide[:, N:] == 7.0).all())
+    clear_device_cache()
