@@ -134,6 +134,20 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
                                     int32_t skip_krylov, int32_t* orders_host, int32_t nobs,
                                     rmb_operator** obs, double* expval_host, void* stream);
 
+/* Many steps in one call (extension; the reference drives this loop from Python, examples/ocs_alignment.py:
+ * 89-100): for step i, the field products of the `ndyn` time-dependent parts are applied
+ * (fprod[(i*ndyn + j)*16 + c], thresh[j], all_dropped[i*ndyn + j]; parts not listed keep their field),
+ * the ensemble is propagated by one step exactly as rmb_propagate_step does (including the skip rule when
+ * every part is screened out), and every `obs_every` steps the per-state expectation values of `nobs`
+ * operators are written to expval_dev[((i / obs_every) * nobs + o) * nstates + s] (complex).  No host
+ * synchronisation per step on the fused path; errors are reported at the end.                           */
+int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld, int32_t nsteps,
+                           double fac_re, double fac_im, double tol, int32_t maxorder,
+                           const double* h0phase_dev, int32_t ndyn, const int32_t* dyn_part,
+                           const double* fprod, const double* thresh, const int32_t* all_dropped,
+                           int32_t nobs, rmb_operator** obs, int32_t obs_every, double* expval_dev,
+                           int32_t* orders_host, void* stream);
+
 /* K5 -- observables (user code in examples/ocs_alignment.py:99-100, tests/test_tdse.py:66).
  * expval_dev[s] = <psi_s| O |psi_s>  (complex, [nstates]), O given as an operator whose field has
  * been applied (rank-0 tensors: fprod = {1}).                                                       */

@@ -57,6 +57,10 @@ SYMBOLS = {
                                                 C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p,
                                                 C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p),
                                                 C.c_void_p, C.c_void_p]),
+    "rmb_propagate_many": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double,
+                                       C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_int32, c_i32p, c_f64p,
+                                       c_f64p, c_i32p, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "rmb_expectation": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rmb_populations": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rmb_set_workspace_budget": (C.c_int32, [C.c_void_p, C.c_int64]),

@@ -1025,7 +1025,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         (long long)nstates * n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30)) {
         if ((rc = ensure_workspace(op, nstates, maxorder))) return rc;
         if ((rc = ensure_slab(op, maxorder, st))) return rc;
-        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
+        if (!op->defer_error) RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
         FusedArgs fa;
         fa.n = n;
         fa.row_blk = op->d_row_blk;
@@ -1055,6 +1055,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         op->n_iterations++;
         if (orders_host)
             RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * nstates, cudaMemcpyDeviceToHost, st));
+        if (op->defer_error) return RMB_OK;      // rmb_propagate_many checks the flag once at the end
         RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
         RMB_CUDA(cudaStreamSynchronize(st));
         if (op->h_ctrl[0]) {
@@ -1148,6 +1149,70 @@ int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, i
     }
     return propagate_device(op, (cplx*)psi_dev, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder,
                             (const cplx*)h0phase_dev, skip_krylov, orders_host, (cudaStream_t)stream);
+}
+
+int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld, int32_t nsteps,
+                           double fac_re, double fac_im, double tol, int32_t maxorder,
+                           const double* h0phase_dev, int32_t ndyn, const int32_t* dyn_part,
+                           const double* fprod, const double* thresh, const int32_t* all_dropped,
+                           int32_t nobs, rmb_operator** obs, int32_t obs_every, double* expval_dev,
+                           int32_t* orders_host, void* stream) {
+    if (!op || !psi_dev || ld < op->n || nstates < 0 || nsteps < 0 || ndyn < 0 || nobs < 0 ||
+        (ndyn > 0 && (!dyn_part || !fprod || !thresh || !all_dropped)) || (nobs > 0 && (!obs || !expval_dev))) {
+        set_error("propagate_many: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    for (int j = 0; j < ndyn; ++j)
+        if (dyn_part[j] < 0 || dyn_part[j] >= (int)op->parts.size() || op->parts[dyn_part[j]].ncart > 16) {
+            set_error("propagate_many: bad time-dependent part");
+            return RMB_ERR_INVALID;
+        }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (obs_every < 1) obs_every = 1;
+    const cplx fac = make_double2(fac_re, fac_im);
+    int result = RMB_OK, rc;
+    // the fused path needs its workspace before the flag can be deferred
+    const bool fused = op->fused_ok && nstates <= 65535 && nstates > 0 &&
+                       (long long)nstates * op->n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30);
+    if (fused) {
+        if ((rc = ensure_workspace(op, nstates, maxorder))) return rc;
+        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
+        op->defer_error = true;
+    }
+    for (int i = 0; i < nsteps; ++i) {
+        for (int j = 0; j < ndyn; ++j) {
+            rc = rmb_operator_set_field(op, dyn_part[j], fprod + ((size_t)i * ndyn + j) * 16, thresh[j],
+                                        all_dropped[(size_t)i * ndyn + j], stream);
+            if (rc != RMB_OK) { op->defer_error = false; return rc; }
+        }
+        int skip = 1;
+        for (auto& p : op->parts) skip = skip && p.has_field && p.all_dropped;
+        if (op->parts.empty()) skip = 1;
+        if (skip && !h0phase_dev) skip = 0;            // without H0 the reference always runs the Krylov part
+        rc = propagate_device(op, (cplx*)psi_dev, nstates, ld, fac, tol, maxorder, (const cplx*)h0phase_dev, skip,
+                              (i == nsteps - 1) ? orders_host : nullptr, st);
+        if (rc == RMB_ERR_MAXORDER) result = rc;
+        else if (rc != RMB_OK) { op->defer_error = false; return rc; }
+        if (nobs > 0 && (i % obs_every) == obs_every - 1) {
+            for (int o = 0; o < nobs; ++o) {
+                rc = rmb_expectation(obs[o], psi_dev, nstates, ld,
+                                     expval_dev + 2 * (((size_t)(i / obs_every) * nobs + o) * (size_t)nstates), stream);
+                if (rc != RMB_OK) { op->defer_error = false; return rc; }
+            }
+        }
+    }
+    if (fused) {
+        op->defer_error = false;
+        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if (op->h_ctrl[0]) result = RMB_ERR_MAXORDER;
+    }
+    if (result == RMB_ERR_MAXORDER) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
+        set_error(buf);
+    }
+    return result;
 }
 
 int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host, double* psi_out_host,

@@ -120,6 +120,7 @@ struct rmb_operator {
 
     // ---- fused single-launch Lanczos step (linear rotors, small N): row -> block tables
     bool fused_ok = false;
+    bool defer_error = false;        // multi-step mode: no per-step synchronisation for the maxorder flag
     int* d_row_blk = nullptr;
     int* d_blk_begin = nullptr;
     long long* d_blk_off = nullptr;

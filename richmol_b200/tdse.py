@@ -342,6 +342,113 @@ class TDSE():
         return vout
 
 
+    # ------------------------------------------------------------------------------------------
+    def propagate(self, terms, vecs, H0=None, tol=1e-15, expect=(), every=1):
+        """Extension: many `update` steps in one call (the time loop of examples/ocs_alignment.py:89-100
+        without returning to Python after every step).
+
+        terms : list of (tensor, fields, thresh) -- the Hamiltonian is the sum of the tensors;
+                `fields` is an array (nsteps, 3) of field vectors at the interval centres for a
+                time-dependent term (thresh as in `CarTens.field`), or None for a static term whose field
+                was applied beforehand (e.g. the dc part of ocs_mixed_field.py).
+        expect : observables evaluated every `every` steps on the propagated states.
+        Returns (vecs, times, expvals[nsteps // every, len(expect), nstates]); `vecs` lives where the input
+        lives (numpy array or CUDA tensor).  Each step is exactly one `update(sum(terms), vecs, H0=H0)`."""
+        import ctypes as C
+        import torch
+        from .field import device_operator
+        from .packing import field_products
+        terms = [(_as_cartens(t, {}), f, th) for (t, f, th) in terms]
+        nsteps = None
+        for _, f, _ in terms:
+            if f is not None:
+                f = np.asarray(f, dtype=np.float64)
+                if f.ndim != 2 or f.shape[1] < 3:
+                    raise IndexError("fields must be an array (nsteps, 3) of X, Y, Z components")
+                if nsteps is not None and len(f) != nsteps:
+                    raise ValueError("all time-dependent terms need the same number of steps")
+                nsteps = len(f)
+        if nsteps is None:
+            raise ValueError("at least one term must be time dependent")
+        first = terms[0][0]
+        basis = first._basis()
+        parts, dyn, static_states = [], [], []
+        for it, (t, f, th) in enumerate(terms):
+            if t._basis().key() != basis.key():
+                raise ValueError("tensors defined with respect to different basis sets")
+            p = t._parts()
+            if len(p) != 1:
+                raise TypeError("terms must be plain tensors (not sums)")
+            parts.append(p[0][0])
+            if f is None:
+                if p[0][1] is None:
+                    raise AttributeError("a static term needs its field applied beforehand")
+                static_states.append(p[0][1])
+            else:
+                dyn.append(it)
+                static_states.append(None)
+        stream = _stream_ptr()
+        op = device_operator(basis, parts)
+        ndyn = len(dyn)
+        fprod = np.zeros((nsteps, ndyn, 16), dtype=np.float64)
+        dropped = np.zeros((nsteps, ndyn), dtype=np.int32)
+        thresh = np.zeros(ndyn, dtype=np.float64)
+        for j, it in enumerate(dyn):
+            t, f, th = terms[it]
+            thresh[j] = 0.0 if th is None else float(th)
+            if len(t.cart) > 16:
+                raise NotImplementedError("tensors with more than 16 Cartesian components")
+            f = np.asarray(f, dtype=np.float64)
+            for i in range(nsteps):
+                fp, dr = field_products(t.cart, f[i], th)
+                fprod[i, j, :len(fp)] = fp
+                dropped[i, j] = int(dr)
+        # static parts: apply their field once; dynamic parts get a placeholder state (overwritten per step)
+        from .field import FieldState
+        op.apply_fields([fs if fs is not None else FieldState(np.zeros(len(terms[k][0].cart)), None, True)
+                         for k, fs in enumerate(static_states)], stream)
+        for it in dyn:
+            op._applied[it] = -1          # the C loop leaves its own field in these parts
+        exp_fac = self._exp_fac()
+        phase_dev = None
+        is_tensor = isinstance(vecs, torch.Tensor)
+        if is_tensor:
+            if not vecs.is_cuda or vecs.dtype != torch.complex128 or vecs.dim() != 2:
+                raise TypeError("device `vecs` must be a 2D CUDA tensor of dtype complex128")
+            work = vecs.clone().contiguous()
+        else:
+            work = torch.from_numpy(np.ascontiguousarray(vecs, dtype=np.complex128)).cuda()
+        if work.shape[1] != basis.N:
+            raise ValueError(f"vecs has {work.shape[1]} columns, the basis has dimension {basis.N}")
+        if H0 is not None:
+            self._h0_phase(_as_cartens(H0, self._cache), exp_fac)
+            phase_dev = self._h0_phase_device(work.device)
+        obs = [_as_cartens(O, {}) for O in expect]
+        for O in obs:
+            if not O._has_field() and getattr(O, "cart", [None])[0] == "0":
+                O.field([0, 0, 1])
+        handles = (C.c_void_p * max(1, len(obs)))(*[O._device(stream).handle for O in obs])
+        nst = work.shape[0]
+        nout = nsteps // max(1, every)
+        expv = torch.zeros((max(nout, 1), max(len(obs), 1), nst), dtype=torch.complex128, device=work.device)
+        dyn_arr = np.array(dyn, dtype=np.int32)
+        orders = torch.zeros(max(nst, 1), dtype=torch.int32).pin_memory()
+        status = _lib.lib().rmb_propagate_many(
+            op.handle, work.data_ptr(), nst, basis.N, nsteps, exp_fac.real, exp_fac.imag, float(tol), 100,
+            phase_dev.data_ptr() if phase_dev is not None else None, ndyn, _lib.ptr(dyn_arr, C.c_int32),
+            _lib.ptr(fprod, C.c_double), _lib.ptr(thresh, C.c_double), _lib.ptr(dropped, C.c_int32),
+            len(obs), handles, max(1, every), expv.data_ptr(), orders.data_ptr(), stream)
+        self._orders = (orders, nst, torch.cuda.current_stream(work.device))
+        _lib.check(status)
+        icall = self._ncalls.setdefault('update', 0)
+        times = np.array([self._time_grid[1][icall + i] for i in range(nsteps)])
+        self._ncalls['update'] = icall + nsteps
+        expv = expv[:nout, :len(obs)]
+        if is_tensor:
+            return work, times, expv
+        return work.cpu().numpy(), times, expv.cpu().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # K5: observables on device-resident ensembles (user code in examples/ocs_alignment.py:99-100,
 # examples/ocs_mixed_field.py:112-117, tests/test_tdse.py:66 does this on the host per state)

@@ -556,3 +556,34 @@ def test_sub_batching_and_strided_states():
     assert torch.equal(wide[:, :N], ref)
     assert bool((wide[:, N:] == 7.0).all())
     clear_device_cache()
+
+
+def test_propagate_many_equals_step_by_step():
+    """The multi-step entry point is a loop of `update` calls: same states bit for bit (fused and batched
+    paths), same skip rule, same observables."""
+    for build, dyn_scale in ((lambda: synth.ocs(10), 6e9), (lambda: synth.h2o(4), 3e9)):
+        m = build()
+        h0, dip, pol, cos2 = m["h0"], m["dip"] * (-AUDIP), m["pol"] * (-0.5 * AUPOL), m["cos2"]
+        dc = [2e6, 0.0, 3e6]
+        dip.field(dc)
+        nsteps = 12
+        fields = np.array([[0.0, 0.1 * dyn_scale * np.sin(i), dyn_scale * np.exp(-((i - 5) / 2.5) ** 2)]
+                           for i in range(nsteps)])
+        fields[10] = [1.0, 2.0, 3.0]                 # screened out by thresh: phases only
+        t1 = TDSE(t_end=10, dt=0.01)
+        t1.time_grid()
+        vecs0 = t1.init_state(h0, temp=5.0)[:7]
+        v = vecs0.copy()
+        ev_ref = []
+        for i in range(nsteps):
+            pol.field(fields[i], thresh=1e2)
+            v, t = t1.update(dip + pol, v, H0=h0)
+            if i % 3 == 2:
+                ev_ref.append(expectation(cos2, v))
+        t2 = TDSE(t_end=10, dt=0.01)
+        t2.time_grid()
+        out, times, ev = t2.propagate([(dip, None, None), (pol, fields, 1e2)], vecs0, H0=h0, expect=[cos2], every=3)
+        assert np.array_equal(out, v)
+        assert abs(times[-1] - t) < 1e-12 and len(times) == nsteps
+        assert relerr(ev[:, 0, :], np.array(ev_ref)) < 1e-14
+        assert np.array_equal(t2.last_orders, t1.last_orders)
