@@ -12,6 +12,7 @@
 #include "rmb_matvec.cuh"
 #include "rmb_fused.cuh"
 #include "rmb_matvec_gemm.cuh"
+#include "rmb_matvec_lin.cuh"
 
 namespace rmb {
 
@@ -64,6 +65,11 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_blk_begin);
     cudaFree(op->d_blk_off);
     cudaFree(op->d_blk_dm);
+    cudaFree(op->d_prod_ket);
+    cudaFree(op->d_lin_blk);
+    cudaFree(op->d_lin_flat);
+    cudaFree(op->d_lin_val);
+    cudaFree(op->d_lin_val_off);
     cudaFree(op->d_items2);
     cudaFree(op->d_itemsG);
     cudaFree(op->d_unitsG);
@@ -115,6 +121,34 @@ void rmb_operator_destroy(rmb_operator* op) {
         cudaEventDestroy(e.second);
     }
     delete op;
+}
+
+// Linear-rotor kernel: bound of the entries per bra block for the fields currently applied (a diagonal can
+// only survive the contraction if a Cartesian component with a non-zero field product has a coefficient on
+// it), and the number of entry buffers that fit next to the ring.
+static constexpr size_t LIN_SMEM_MAX = 226 * 1024;
+static void lin_update_bound(rmb_operator* op) {
+    if (!op->lin_ok) return;
+    const int ntab = (int)op->h_tab_part.size();
+    std::vector<int> alive(ntab, 0);
+    for (int t = 0; t < ntab; ++t) {
+        const PartH& ph = op->parts[op->h_tab_part[t]];
+        const unsigned nz = ph.has_field ? (ph.all_dropped ? 0u : ph.nzmask) : 0xffffffffu;
+        int n = 0;
+        for (int j = op->h_diag_off[t]; j < op->h_diag_off[t + 1]; ++j) n += (op->h_diag_cart[j] & nz) ? 1 : 0;
+        alive[t] = std::min(n, MV2_NDMAX);
+    }
+    long long ebuf = 1;
+    for (int b = 0; b < op->nblocks; ++b) {
+        long long l = 0;
+        for (int p = op->h_bra_begin[b]; p < op->h_bra_begin[b + 1]; ++p) l += alive[op->h_prods[p].tab];
+        ebuf = std::max(ebuf, std::min<long long>(l, ML_LMAX) * op->h_blk_dm[b]);
+    }
+    op->lin_ebuf_cur = (int)std::min<long long>(ebuf, op->lin_ebuf);
+    const size_t per = (size_t)op->lin_ebuf_cur * 16 + ML_FLAT * sizeof(LinEnt);
+    int nb = (int)((LIN_SMEM_MAX - op->lin_smem_fixed) / per);
+    op->lin_NB = std::max(2, std::min(nb, ML_NBMAX));
+    op->lin_smem = op->lin_smem_fixed + (size_t)op->lin_NB * per;
 }
 
 int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
@@ -201,6 +235,24 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             kpool.insert(kpool.end(), pd.kpool, pd.kpool + pd.kpool_len * (pd.k_is_complex ? 2 : 1));
         }
         for (int t = 0; t < pd.ntables; ++t) op->nd_max = std::max(op->nd_max, pd.tb_nd[t]);
+        // per (table, diagonal): which Cartesian components can make it non-zero (host-side upper bound of the
+        // device's diagonal masks, used to size the entry buffers of the linear-rotor kernel)
+        for (int t = 0; t < pd.ntables; ++t) {
+            const int nd = pd.tb_nd[t];
+            if (op->h_diag_off.empty()) op->h_diag_off.push_back(0);
+            const size_t base = op->h_diag_cart.size();
+            op->h_diag_cart.resize(base + nd, 0u);
+            for (long long e = pd.tb_off[t]; e < pd.tb_off[t + 1]; ++e) {
+                if (pd.ent_col[e] < 0) continue;
+                const int j = (int)((e - pd.tb_off[t]) % nd);
+                for (int c = 0; c < pd.ncart && c < 32; ++c) {
+                    const double* v = pd.ent_coef + 2 * ((size_t)c * nent + e);
+                    if (v[0] != 0.0 || v[1] != 0.0) op->h_diag_cart[base + j] |= 1u << c;
+                }
+            }
+            op->h_diag_off.push_back((int)op->h_diag_cart.size());
+            op->h_tab_part.push_back(q);
+        }
         for (int p = 0; p < pd.nprod; ++p) {
             const int b1 = pd.pr_bra[p], b2 = pd.pr_ket[p], t = pd.pr_table[p];
             if (b1 < 0 || b1 >= d->nblocks || b2 < 0 || b2 >= d->nblocks || t < 0 || t >= pd.ntables) {
@@ -241,6 +293,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return hp[a].bra < hp[b].bra; });
     op->h_prods.resize(hp.size());
+    std::vector<int> h_prod_ket, h_prod_bra;
     std::vector<int> bra_begin(d->nblocks + 1, 0);
     for (size_t i = 0; i < perm.size(); ++i) {
         const HProd& h = hp[perm[i]];
@@ -252,6 +305,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         pr.dm2 = d->blk_dm[h.ket];
         pr.nd = h.nd;
         pr.tab = h.tab;
+        h_prod_ket.push_back(h.ket);
+        h_prod_bra.push_back(h.bra);
         op->h_prod_dm1.push_back(d->blk_dm[h.bra]);
         op->h_prod_dk1.push_back(d->blk_dk[h.bra]);
         bra_begin[h.bra + 1]++;
@@ -602,6 +657,88 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             const char* ff = getenv("RMB_FUSED");
             op->fused_ok = !(ff && strcmp(ff, "0") == 0);
         }
+        // sliding-window matvec for large ensembles of linear rotors
+        int W = 0, dmmax = 1;
+        for (size_t p = 0; p < h_prod_ket.size(); ++p) W = std::max(W, std::abs(h_prod_ket[p] - h_prod_bra[p]));
+        for (int b = 0; b < d->nblocks; ++b) dmmax = std::max(dmmax, d->blk_dm[b]);
+        dmmax |= 1;                                               // odd row stride: conflict-free lanes
+        const char* fl = getenv("RMB_LIN");
+        int maxL = 0;
+        for (int b = 0; b < d->nblocks; ++b) {
+            int l = 0;
+            for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) l += std::min(op->h_prods[p].nd, MV2_NDMAX);
+            maxL = std::max(maxL, l);
+        }
+        if (all1 && W <= 3 && op->nd_max <= MV2_NDMAX && op->nprod > 0 && maxL <= ML_LMAX &&
+            !(fl && strcmp(fl, "0") == 0)) {
+            // per-block entry capacity (all diagonals alive) and offsets of the folded K*MF values
+            std::vector<long long> val_off(d->nblocks + 1, 0);
+            long long ebuf_elems = 1;
+            for (int b = 0; b < d->nblocks; ++b) {
+                int l = 0;
+                for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) l += std::min(op->h_prods[p].nd, MV2_NDMAX);
+                const long long cap = (long long)l * d->blk_dm[b];
+                val_off[b + 1] = val_off[b] + cap;
+                ebuf_elems = std::max(ebuf_elems, cap);
+            }
+            // T = 8 states per CTA (two groups of 4 per thread) with a ring of up to 2W+4 ket blocks (prefetch depth)
+            for (int pass = 0; pass < 6 && !op->lin_ok; ++pass) {
+                const int T = pass < 3 ? 8 : 4;
+                const int NS = 2 * W + 4 - pass % 3;
+                const size_t fixed = (size_t)NS * T * dmmax * 16 + (size_t)(2 * NS + ML_NBMAX + 1) * 8 +
+                                     (size_t)d->nblocks * sizeof(LinBlk) + 128;
+                const size_t need = fixed + (size_t)2 * (ebuf_elems * 16 + ML_FLAT * sizeof(LinEnt));
+                if (need <= LIN_SMEM_MAX) {
+                    op->lin_smem_fixed = fixed;
+                    op->lin_ok = true;
+                    op->lin_W = W;
+                    op->lin_T = T;
+                    op->lin_NS = NS;
+                    op->lin_dm_max = dmmax;
+                    op->lin_smem = need;
+                    op->lin_ebuf = (int)ebuf_elems;
+                }
+            }
+            if (op->lin_ok && op->nent >= (1ll << 31)) op->lin_ok = false;
+            if (op->lin_ok) {
+                if (!op->d_blk_begin) {
+                    std::vector<long long> boff(d->nblocks);
+                    for (int b = 0; b < d->nblocks; ++b) boff[b] = d->blk_off[b];
+                    if ((rc = upload(&op->d_blk_begin, bra_begin.data(), bra_begin.size()))) return rc;
+                    if ((rc = upload(&op->d_blk_off, boff.data(), boff.size()))) return rc;
+                    if ((rc = upload(&op->d_blk_dm, d->blk_dm, (size_t)d->nblocks))) return rc;
+                }
+                if ((rc = upload(&op->d_prod_ket, h_prod_ket.data(), h_prod_ket.size()))) return rc;
+                std::vector<LinBlk> lb(d->nblocks);
+                int chunk0 = 0, ubase = 0;
+                const int G = op->lin_T / std::min(op->lin_T, ML_TS);
+                for (int b = 0; b < d->nblocks; ++b) {
+                    const int nch = (d->blk_dm[b] + 31) / 32;
+                    lb[b].off = poff[b];
+                    lb[b].val_off = val_off[b];
+                    lb[b].dm = d->blk_dm[b];
+                    lb[b].chunk0 = chunk0;
+                    lb[b].ubase = ubase;
+                    lb[b].L = 0;
+                    chunk0 += nch;
+                    ubase = (ubase + nch * G) % ML_CWARPS;
+                }
+                op->lin_npart = chunk0;
+                if ((rc = upload((LinBlk**)&op->d_lin_blk, lb.data(), lb.size()))) return rc;
+                RMB_CUDA(cudaMalloc(&op->d_lin_flat, (size_t)d->nblocks * ML_FLAT * sizeof(LinEnt)));
+                if ((rc = upload(&op->d_lin_val_off, val_off.data(), val_off.size()))) return rc;   // k_lin_entries
+                RMB_CUDA(cudaMalloc((void**)&op->d_lin_val, (size_t)std::max<long long>(1, val_off[d->nblocks]) * sizeof(cplx)));
+                static bool g_lin_attr = false;
+                if (!g_lin_attr) {
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
+                    g_lin_attr = true;
+                }
+                op->h_bra_begin = bra_begin;
+                op->h_blk_dm.assign(d->blk_dm, d->blk_dm + d->nblocks);
+                lin_update_bound(op);
+            }
+        }
     }
     if ((rc = upload((ItemG**)&op->d_itemsG, itemsG.data(), itemsG.size()))) return rc;
     {
@@ -688,9 +825,17 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
             op->d_tab_mask, op->d_ent_cent);
         RMB_CUDA(cudaGetLastError());
         op->n_launches += 2;
+        op->lin_flat_dirty = true;
     }
     ph.has_field = true;
+    {
+        unsigned nz = 0;
+        for (int c = 0; c < ph.ncart && c < 32; ++c)
+            if (fprod[c] != 0.0) nz |= 1u << c;
+        ph.nzmask = nz;
+    }
     ph.all_dropped = all_dropped != 0;
+    op->lin_flat_dirty = true;
     return RMB_OK;
 }
 
@@ -740,6 +885,7 @@ struct MvEpilogue {
     int scale_stride = 0;
     cplx* pdot = nullptr;            // fused partial sums conj(y) * x per (state, tiled item)
     int npart = 0;
+    bool use_lin = false;            // sliding-window kernel for linear rotors (npart = nblocks)
 };
 
 static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
@@ -757,6 +903,43 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             RMB_CUDA(cudaEventCreate(&ev.second));
         }
         RMB_CUDA(cudaEventRecord(ev.first, st));
+    }
+    if (ep.use_lin && op->lin_ok) {
+        LinArgs la;
+        la.nblocks = op->nblocks;
+        la.W = op->lin_W;
+        la.dms = op->lin_dm_max;
+        la.NS = op->lin_NS;
+        if (op->lin_flat_dirty) lin_update_bound(op);
+        la.NB = op->lin_NB;
+        la.ebuf_elems = op->lin_ebuf_cur;
+        la.blk = (const LinBlk*)op->d_lin_blk;
+        la.flat = (const LinEnt*)op->d_lin_flat;
+        la.val = op->d_lin_val;
+        const int T = op->lin_T;
+        if (op->lin_flat_dirty) {
+            k_lin_entries<<<(unsigned)op->nblocks, 128, 0, st>>>(
+                op->nblocks, op->lin_NS, (unsigned)(T * op->lin_dm_max * 16), op->d_blk_begin, op->d_blk_dm,
+                op->d_prod_ket, op->d_prods, op->d_tab_mask, (const MfEntry*)op->d_ent_cent, op->d_kpool,
+                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val);
+            op->lin_flat_dirty = false;
+            op->n_launches++;
+        }
+        const unsigned grid = (unsigned)((nstates + T - 1) / T);
+        if (T == 8)
+            k_matvec_lin<8><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                    ep.scale_stride, ep.pdot, ep.npart);
+        else
+            k_matvec_lin<4><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                    ep.scale_stride, ep.pdot, ep.npart);
+        op->n_launches++;
+        RMB_CUDA(cudaGetLastError());
+        if (op->time_matvec) {
+            RMB_CUDA(cudaEventRecord(ev.second, st));
+            op->mv_events.push_back(ev);
+        }
+        op->n_matvec_launches++;
+        return RMB_OK;
     }
     if (op->nitems2 > 0) {
         // work units (item, first state) for this batch size; rebuilt only when the size changes
@@ -860,7 +1043,7 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     op->nchunk = nchunks(op->np);
     int rc;
     const size_t vec = (size_t)cap * (size_t)op->np;
-    const size_t np = (size_t)std::max(op->nchunk, op->nitems2 + op->nitemsG);
+    const size_t np = (size_t)std::max({op->nchunk, op->nitems2 + op->nitemsG, op->lin_npart});
     if ((rc = ensure(&op->d_w, vec))) return rc;
     RMB_CUDA(cudaMemset(op->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
     if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
@@ -926,8 +1109,9 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     const dim3 vgrid((unsigned)nch, (unsigned)B);          // padded vectors
     const dim3 ugrid((unsigned)nchunks(n), (unsigned)B);   // user-layout vectors
     const int ts = op->ws_maxorder, bs = op->ws_maxorder + 1;
-    const bool fused = fused_dot(op);
-    const int npart = dot_parts(op);
+    const bool lin = op->lin_ok && B >= 4 * op->lin_T;      // large batches of linear rotors: sliding window
+    const bool fused = lin || fused_dot(op);
+    const int npart = lin ? op->lin_npart : dot_parts(op);
     int rc;
     if ((rc = ensure_slab(op, 2, st))) return rc;
     RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
@@ -935,7 +1119,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
                                                                op->d_beta, bs, (int)B);
     k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], np, n, op->d_pmap);
     op->n_launches += 2;
-    int k = 0, last = -1;
+    int k = 0;
     std::vector<long long> act_hist;
     for (;; ++k) {
         if ((rc = ensure_slab(op, k + 1, st))) return rc;
@@ -946,6 +1130,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             ep.scale_stride = bs;
             ep.pdot = op->d_pdot;
             ep.npart = npart;
+            ep.use_lin = lin;
         }
         if ((rc = launch_matvec(op, Vk, op->d_w, B, np, np, op->d_active, st, ep))) return rc;
         if (!fused) {
@@ -972,14 +1157,13 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             RMB_CUDA(cudaEventSynchronize(op->it_events[k - 1]));
             act_hist.push_back(op->h_ctrl[4 * (k - 1)]);
             if (op->h_ctrl[4 * (k - 1) + 1]) *hit_maxorder = true;
-            if (op->h_ctrl[4 * (k - 1)] == 0) { last = k - 1; break; }
+            if (op->h_ctrl[4 * (k - 1)] == 0) break;
         }
         if (k + 1 >= maxorder + 1) {   // safety net: cannot happen (k_small_b retires every state)
             RMB_CUDA(cudaEventSynchronize(op->it_events[k]));
             break;
         }
     }
-    (void)last;
     k_combine<<<ugrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, np, n, op->d_ceff, ts, op->d_order, ph, psi, ld,
                                              op->d_pmap);
     op->n_launches++;
@@ -1131,7 +1315,9 @@ int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t
         // user layout -> padded scratch, product, back
         k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)x_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
                                                     op->d_pmap);
-        if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st))) return rc;
+        MvEpilogue epm;
+        epm.use_lin = op->lin_ok && b >= 4 * op->lin_T;
+        if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st, epm))) return rc;
         k_unpad<<<ugrid, VEC_THREADS, 0, st>>>(op->d_w, np, (cplx*)y_dev + s0 * ld, ld, n, op->d_pmap);
         op->n_launches += 2;
         op->n_state_matvecs += b;
@@ -1332,12 +1518,14 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
         k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
                                                     op->d_pmap);
         op->n_launches++;
-        if (fused_dot(op)) {
+        if (fused_dot(op) || op->lin_ok) {
             // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
             // the product vector itself is never written
             MvEpilogue ep;
             ep.pdot = op->d_pdot;
-            ep.npart = dot_parts(op);
+            ep.use_lin = op->lin_ok && b >= 4 * op->lin_T;
+            ep.npart = ep.use_lin ? op->lin_npart : dot_parts(op);
+            if (!ep.use_lin && !fused_dot(op)) { set_error("internal: unfused expectation"); return RMB_ERR_INVALID; }
             if ((rc = launch_matvec(op, op->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;

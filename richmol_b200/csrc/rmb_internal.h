@@ -46,6 +46,7 @@ struct PartH {
     double* d_fprod = nullptr;              // [ncart]
     bool has_field = false;
     bool all_dropped = false;
+    unsigned nzmask = 0xffffffffu;          // Cartesian components with a non-zero field product
 };
 
 void set_error(const std::string& msg);
@@ -125,6 +126,25 @@ struct rmb_operator {
     int* d_blk_begin = nullptr;
     long long* d_blk_off = nullptr;
     int* d_blk_dm = nullptr;
+
+    // ---- sliding-window matvec for linear rotors (rmb_matvec_lin.cuh)
+    bool lin_ok = false;
+    int lin_W = 0, lin_T = 0, lin_dm_max = 0, lin_NS = 0, lin_npart = 0;
+    size_t lin_smem = 0;
+    bool lin_flat_dirty = true;      // entry lists must be rebuilt (field changed)
+    int* d_prod_ket = nullptr;
+    void* d_lin_blk = nullptr;       // LinBlk[nblocks]
+    void* d_lin_flat = nullptr;      // LinEnt[nblocks][ML_FLAT]
+    long long* d_lin_val_off = nullptr;
+    rmb::cplx* d_lin_val = nullptr;  // K * MF per (block, entry, row), rebuilt after every field update
+    int lin_ebuf = 0;                // worst-case elements of one entry buffer (every diagonal alive)
+    int lin_ebuf_cur = 0, lin_NB = 2;    // bound for the fields currently applied, entry buffers that fit
+    size_t lin_smem_fixed = 0;       // ring + barriers + block table
+    std::vector<unsigned> h_diag_cart;   // per (table, diagonal): Cartesian components with a non-zero coefficient
+    std::vector<int> h_diag_off;     // [ntables + 1] offsets into h_diag_cart
+    std::vector<int> h_tab_part;     // [ntables] part owning the table
+    std::vector<int> h_bra_begin;    // [nblocks + 1] products sorted by bra block
+    std::vector<int> h_blk_dm;       // [nblocks]
 
     // ---- Krylov workspace (lazily sized) ----
     long long ws_budget = 0;         // bytes; 0 = auto

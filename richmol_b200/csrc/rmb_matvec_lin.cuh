@@ -1,0 +1,320 @@
+// K2 (linear rotors, dim_k = 1 everywhere): HBM-bound H.Psi for large ensembles.
+//
+// For dim_k = 1 the operator data (10-25 MF entries per row) outweighs the state data (16 B per row and
+// state), and the J +- 2 band makes every row tile re-read its ket halo.  This kernel removes both:
+//  * a persistent CTA owns a tile of T states and walks the (J,sym) blocks in order, keeping a ring of
+//    >= 2W+2 ket blocks in shared memory (W = block bandwidth of the operator): every element of Psi is
+//    read from HBM exactly once (TMA bulk copies issued by a producer warp, one per state and block,
+//    completing on per-slot mbarriers) and every element of the product is written once;
+//  * the operator is streamed the same way: after every field update k_lin_entries folds the 1 x 1 K factors
+//    into the surviving MF diagonals and lays them out per bra block as [entry][row]; the producer warp
+//    brings the block's entries in with ONE bulk copy, two blocks ahead of their use;
+//  * lanes run over the rows of a block (entry rows and ket rows are then consecutive shared-memory words:
+//    bank-conflict free); ring tiles are [state][row].
+// The epilogue applies the per-state scale, stores the product with coalesced rows and produces the partial
+// sums conj(y).x of the Lanczos recurrence per (state, 32-row chunk).
+#pragma once
+#include "rmb_matvec.cuh"
+
+namespace rmb {
+
+constexpr int ML_CWARPS = 15;                        // compute warps
+constexpr int ML_XPROD = 1;               // producer warps for the ket blocks (block j -> warp j % ML_XPROD)
+constexpr int ML_THREADS = (ML_CWARPS + ML_XPROD + 1) * 32;   // + producer warps (TMA bulk copies: ket blocks, entries)
+constexpr int ML_TS = 4;                             // states per thread
+constexpr int ML_LMAX = 40;                          // max (product, diagonal) entries per bra block
+constexpr int ML_NBMAX = 4;                          // entry buffers: 2 .. 4, as many as fit next to the ring
+
+// one (product, surviving diagonal) of a bra block: byte offset of the ket block's ring slot, diagonal offset
+// (col - row) and rows of the ket block.  Record 0 of every per-block list is a header: xbyte = number of
+// entries that follow.
+struct __align__(16) LinEnt { unsigned xbyte; int doff; int dm2; int pad; };
+constexpr int ML_FLAT = ML_LMAX + 1;                 // LinEnt records per bra block (header + entries)
+
+// static per-block data, copied to shared memory at kernel start
+struct __align__(16) LinBlk {
+    long long off;        // first element of the block in a (padded) state vector
+    long long val_off;    // first element of the block's entries in `val`
+    int dm;               // rows
+    int chunk0;           // index of the block's first 32-row chunk (partial-dot slot)
+    int ubase;            // (number of units of all earlier blocks) % ML_CWARPS, per state-group count G
+    int L;                // filled in shared memory from the entry-list header
+};
+
+struct LinArgs {
+    int nblocks;
+    int W;                               // |ket block - bra block| <= W for every product
+    int dms;                             // row stride of a state inside a ring slot (odd, >= max dim_m)
+    int NS;                              // ring slots (>= 2W + 2)
+    int NB;                              // entry buffers (2 .. ML_NBMAX)
+    int ebuf_elems;                      // elements of one entry buffer (bound for the field currently applied)
+    const LinBlk* blk;                   // [nblocks] static per-block table
+    const LinEnt* flat;                  // [nblocks][ML_FLAT]
+    const double2* val;                  // K * MF per (block, entry, row): [L_b][dm_b] per block
+};
+
+// After every field update: per bra block, the list of surviving (product, diagonal) pairs and their values
+// K_p * MF_p[row] (zero where the diagonal leaves the ket block).  One CTA per block.
+__global__ void __launch_bounds__(128)
+k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ blk_begin,
+              const int* __restrict__ blk_dm, const int* __restrict__ prod_ket, const ProdD* __restrict__ prods,
+              const unsigned* __restrict__ tab_mask, const MfEntry* __restrict__ cent,
+              const double* __restrict__ kpool, int k_complex, const long long* __restrict__ val_off,
+              LinEnt* __restrict__ flat, double2* __restrict__ val) {
+    __shared__ long long s_ent[ML_LMAX];
+    __shared__ double2 s_k[ML_LMAX];
+    __shared__ int s_L;
+    const int b = blockIdx.x, lane = threadIdx.x & 31;
+    const int p0 = blk_begin[b], p1 = blk_begin[b + 1], dm1 = blk_dm[b];
+    LinEnt* out = flat + (size_t)b * ML_FLAT;
+    if (threadIdx.x < 32) {
+        int L = 0;
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int p = pb + lane;
+            int nnz = 0;
+            ProdD pr;
+            if (p < p1) {
+                pr = prods[p];
+                nnz = min(__popc(tab_mask[pr.tab]), MV2_NDMAX);
+            }
+            int incl = nnz;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int base = L + incl - nnz;
+            if (p < p1 && nnz > 0) {
+                double2 kv = make_double2(0.0, 0.0);
+                if (k_complex) kv = reinterpret_cast<const double2*>(kpool)[pr.koff];
+                else kv.x = kpool[pr.koff];
+                const int ket = prod_ket[p];
+                for (int q = 0; q < nnz; ++q)
+                    if (base + q < ML_LMAX) {
+                        const long long e0 = pr.ent_off + (long long)q * dm1;
+                        LinEnt e;
+                        e.xbyte = (unsigned)(ket % NS) * slot_bytes;
+                        e.doff = 0;                        // from the first row whose entry lies inside the ket block
+                        for (int r = 0; r < dm1; ++r) {
+                            const int c = cent[e0 + r].col;
+                            if (c >= 0) { e.doff = c - r; break; }
+                        }
+                        e.dm2 = blk_dm[ket];
+                        e.pad = 0;
+                        out[1 + base + q] = e;
+                        s_ent[base + q] = e0;
+                        s_k[base + q] = kv;
+                    }
+            }
+            L += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            LinEnt h;
+            h.xbyte = (unsigned)min(L, ML_LMAX);
+            h.doff = h.dm2 = h.pad = 0;
+            out[0] = h;
+            s_L = min(L, ML_LMAX);
+        }
+    }
+    __syncthreads();
+    const int L = s_L;
+    double2* vout = val + val_off[b];
+    for (int i = threadIdx.x; i < L * dm1; i += blockDim.x) {
+        const int j = i / dm1, r = i - j * dm1;
+        const MfEntry e = cent[s_ent[j] + r];
+        const double2 k = s_k[j];
+        vout[i] = e.col >= 0 ? make_double2(k.x * e.re - k.y * e.im, k.x * e.im + k.y * e.re)
+                             : make_double2(0.0, 0.0);
+    }
+}
+
+// Work unit = (bra block b, 32-row chunk c, state group g): one warp, one lane per row m1, ML_TS states per
+// thread; per (entry, state) the inner loop is one LDS.128 and four DFMA.  Units are dealt round-robin to the
+// compute warps across blocks; warps only synchronise through mbarriers (`full`: ket block landed, `efull`:
+// entries landed, `done`: bra block consumed by a warp).
+template <int T>
+__global__ void __launch_bounds__(ML_THREADS, 1)
+k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict__ Y, long long ldx,
+             long long ldy, int nstates, const int* __restrict__ active, const double* __restrict__ scale,
+             int scale_stride, double2* __restrict__ pdot, int npart) {
+    constexpr int TS = T < ML_TS ? T : ML_TS;                 // states per thread
+    constexpr int G = T / TS;                                 // state groups
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NS = a.NS;
+    const int slot_elems = T * a.dms;                         // [state][row]
+    double2* ring = reinterpret_cast<double2*>(smem_raw);                     // [NS][T][dms]
+    double2* ebuf = ring + (size_t)NS * slot_elems;                           // [ML_NB][ebuf_elems]
+    const int NB = a.NB;
+    LinEnt* flat = reinterpret_cast<LinEnt*>(ebuf + (size_t)NB * a.ebuf_elems);      // [NB][ML_FLAT]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(flat + NB * ML_FLAT);   // [NS]
+    unsigned long long* done = full + NS;                                     // [NS]
+    unsigned long long* efull = done + NS;                                    // [NB]
+    LinBlk* blk = reinterpret_cast<LinBlk*>(efull + NB + ((2 * NS + NB) & 1));        // [nblocks], 16-byte aligned
+    __shared__ long long s_sb[T];
+    __shared__ double s_sc[T];
+    __shared__ int s_nact;
+
+    const int s0 = blockIdx.x * T;
+    if (threadIdx.x < T) {
+        const int s = s0 + threadIdx.x;
+        const bool ok = s < nstates && (active == nullptr || active[s]);
+        s_sb[threadIdx.x] = ok ? (long long)s : -1;
+        s_sc[threadIdx.x] = (ok && scale != nullptr) ? scale[(long long)s * scale_stride] : 1.0;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], ML_CWARPS);
+        }
+        for (int i = 0; i < NB; ++i) mbar_init(&efull[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // per-block table: no global metadata loads inside the block loops
+    for (int b = threadIdx.x; b < a.nblocks; b += ML_THREADS) {
+        LinBlk t = a.blk[b];
+        t.L = (int)a.flat[(size_t)b * ML_FLAT].xbyte;
+        blk[b] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int i = 0; i < T; ++i) n += s_sb[i] >= 0 ? 1 : 0;
+        s_nact = n;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (nact == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp >= ML_CWARPS) {
+        // ================= producer warps =================
+        // both observe `done` strictly in block order with their own counters
+        int ds = 0, dph = 0, dcnt = 0;       // slot / phase of the next `done` barrier to observe, its block
+        auto observe = [&](int need) {
+            while (dcnt <= need) {
+                mbar_wait(&done[ds], (unsigned)dph);
+                ++dcnt;
+                if (++ds == NS) { ds = 0; dph ^= 1; }
+            }
+        };
+        if (warp < ML_CWARPS + ML_XPROD) {
+            // ket blocks: lane t copies the block of state t; ring slot of block j is free when every warp
+            // is finished with bra blocks <= j - NS + W
+            const long long sb = lane < T ? s_sb[lane] : -1;
+            const double2* xrow = X + (sb >= 0 ? sb : 0) * ldx;
+            double2* dst = ring + (size_t)lane * a.dms;
+            const int j0 = warp - ML_CWARPS;
+            int xs = j0 % NS;
+            for (int j = j0; j < a.nblocks; j += ML_XPROD) {
+                observe(j - NS + a.W);
+                const LinBlk t = blk[j];
+                unsigned long long* bar = &full[xs];
+                if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)nact * (unsigned)t.dm * 16u);
+                __syncwarp();
+                if (sb >= 0) tma_load_1d(dst + (size_t)xs * slot_elems, xrow + t.off, (unsigned)t.dm * 16u, bar);
+                xs += ML_XPROD;
+                if (xs >= NS) xs -= NS;
+            }
+        } else if (lane == 0) {
+            // entries of bra block eb (descriptor list + K * MF values): buffer free when every warp is
+            // finished with bra block eb - NB
+            int es = 0;
+            for (int eb = 0; eb < a.nblocks; ++eb) {
+                observe(eb - NB);
+                const LinBlk t = blk[eb];
+                const unsigned vbytes = (unsigned)t.L * (unsigned)t.dm * 16u;
+                unsigned long long* bar = &efull[es];
+                mbar_arrive_expect_tx(bar, vbytes + (unsigned)(ML_FLAT * sizeof(LinEnt)));
+                tma_load_1d(flat + es * ML_FLAT, a.flat + (size_t)eb * ML_FLAT, (unsigned)(ML_FLAT * sizeof(LinEnt)), bar);
+                if (vbytes) tma_load_1d(ebuf + (size_t)es * a.ebuf_elems, a.val + t.val_off, vbytes, bar);
+                if (++es == NB) es = 0;
+            }
+        }
+        return;
+    }
+
+    // ================= compute warps =================
+    int waited = -1;                                 // highest ket block whose arrival has been observed
+    int bs = 0;                                      // b % NS
+    int es = 0, eph = 0;                             // b % NB and the phase of its `efull` barrier
+    const char* ring_b = reinterpret_cast<const char*>(ring);
+    const unsigned st_bytes = (unsigned)a.dms * 16u;
+    for (int b = 0; b < a.nblocks; ++b) {
+        const LinBlk bt = blk[b];
+        const int dm1 = bt.dm;
+        const int nunits = ((dm1 + 31) >> 5) * G;
+        int u = warp - bt.ubase;                     // first unit of the block owned by this warp
+        if (u < 0) u += ML_CWARPS;
+        if (u < nunits) {
+            // lazy waits: only the ket blocks this unit reads, b - W .. b + W, and the block's entries.  A slot is
+            // re-armed for block k + NS only after every warp (this one included) has arrived on done(k + W), so
+            // the barriers of blocks >= b - W are still in the phase waited for here, or the one just completed
+            for (int k = max(waited + 1, b - a.W); k <= min(b + a.W, a.nblocks - 1); ++k) {
+                const int q = k / NS;
+                mbar_wait(&full[k - q * NS], (unsigned)q & 1u);
+            }
+            waited = min(b + a.W, a.nblocks - 1);
+            mbar_wait(&efull[es], (unsigned)eph);
+            const LinEnt* fl = flat + es * ML_FLAT;
+            const double2* ev = ebuf + (size_t)es * a.ebuf_elems;
+            const int L = bt.L;
+            const double2* xbra = ring + (size_t)bs * slot_elems;
+            for (; u < nunits; u += ML_CWARPS) {
+                const int c = u / G, g = u - c * G;
+                const int r = c * 32 + lane;
+                const bool rv = r < dm1;
+                const int rr = rv ? r : dm1 - 1;              // idle lanes repeat the last row (never stored)
+                const int tb = g * TS;
+                const unsigned tb_bytes = (unsigned)tb * st_bytes;
+                double2 acc[TS];
+#pragma unroll
+                for (int t = 0; t < TS; ++t) acc[t] = make_double2(0.0, 0.0);
+#pragma unroll 2
+                for (int j = 0; j < L; ++j) {
+                    const LinEnt f = fl[1 + j];
+                    const double2 e = ev[j * dm1 + rr];
+                    const int col = min(max(rr + f.doff, 0), f.dm2 - 1);   // outside the ket block e is zero
+                    const char* xp = ring_b + f.xbyte + tb_bytes + (unsigned)col * 16u;
+                    double2 v[TS];
+#pragma unroll
+                    for (int t = 0; t < TS; ++t) v[t] = *reinterpret_cast<const double2*>(xp + t * st_bytes);
+#pragma unroll
+                    for (int t = 0; t < TS; ++t) {
+                        acc[t].x = fma(e.x, v[t].x, acc[t].x);
+                        acc[t].y = fma(e.x, v[t].y, acc[t].y);
+                        acc[t].x = fma(-e.y, v[t].y, acc[t].x);
+                        acc[t].y = fma(e.y, v[t].x, acc[t].y);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < TS; ++t) {
+                    const long long sg = s_sb[tb + t];
+                    if (sg < 0) continue;                     // warp-uniform
+                    const double sc = s_sc[tb + t];
+                    const double2 y = make_double2(acc[t].x * sc, acc[t].y * sc);
+                    if (Y != nullptr && rv) Y[sg * ldy + bt.off + r] = y;    // lanes = consecutive rows
+                    if (pdot != nullptr) {
+                        double px = 0.0, py = 0.0;
+                        if (rv) {
+                            const double2 v = xbra[(size_t)(tb + t) * a.dms + r];
+                            px = y.x * v.x + y.y * v.y;
+                            py = y.x * v.y - y.y * v.x;
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            px += __shfl_down_sync(0xffffffffu, px, o);
+                            py += __shfl_down_sync(0xffffffffu, py, o);
+                        }
+                        if (lane == 0) pdot[sg * npart + bt.chunk0 + c] = make_double2(px, py);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[bs]);                // this warp is finished with bra block b
+        if (++bs == NS) bs = 0;
+        if (++es == NB) { es = 0; eph ^= 1; }
+    }
+}
+
+}  // namespace rmb

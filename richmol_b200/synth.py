@@ -88,7 +88,12 @@ def cart_to_spher(rank):
                 us[i] += cg * np.kron(u1[a + 1], u1[b + 1])
     else:
         raise NotImplementedError(f"tensor of rank = {rank} is not implemented")
-    return us, np.linalg.pinv(us), os_, list(_CART[rank])
+    # Us is unitary: its pseudo-inverse is exact up to rounding dust (~1e-16), which would otherwise keep
+    # physically absent M diagonals alive (e.g. Delta M = +-1, +-2 for the zz component)
+    us[np.abs(us) < 1e-13] = 0
+    ux = np.linalg.pinv(us)
+    ux[np.abs(ux) < 1e-13] = 0
+    return us, ux, os_, list(_CART[rank])
 
 
 # ----------------------------------------------------------------------------------------------

@@ -587,3 +587,82 @@ def test_propagate_many_equals_step_by_step():
         assert abs(times[-1] - t) < 1e-12 and len(times) == nsteps
         assert relerr(ev[:, 0, :], np.array(ev_ref)) < 1e-14
         assert np.array_equal(t2.last_orders, t1.last_orders)
+
+
+def test_linear_rotor_sliding_window_kernel():
+    """Large ensembles of linear rotors use the sliding-window matvec (ring of ket blocks in shared memory,
+    lanes over rows): matvec, expectation and the batched Lanczos path (RMB_FUSED=0) vs the oracle and vs
+    the fused single-launch path."""
+    import os
+    import torch
+    from richmol_b200.field import clear_device_cache
+    m = synth.ocs(14)
+    h0, cos2 = m["h0"], m["cos2"]
+    dc = [3e6, 0.0, 5e6]
+    ac = [2e9, -1e9, 6e9]                      # general polarisation: complex MF, five diagonals
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    N = h0._basis().N
+    vecs = random_states(150, N, seed=41)      # ragged: 150 = 18 tiles of 8 + 6
+
+    def build():
+        mm = synth.ocs(14)
+        Hdc, Hac = mm["dip"] * (-AUDIP), mm["pol"] * (-0.5 * AUPOL)
+        Hdc.field(dc)
+        Hac.field(ac, thresh=1e2)
+        return Hdc + Hac, mm["cos2"]
+    H, c2 = build()
+    odc, oac = oracle_of(m["dip"]).scaled(-AUDIP), oracle_of(m["pol"]).scaled(-0.5 * AUPOL)
+    odc.field(dc)
+    oac.field(ac, thresh=1e2)
+    oH = odc.add(oac)
+    # matvec (>= 64 states: sliding window) against the oracle
+    y = gpu_matvec(H, vecs)
+    yo = np.array([port.flat_matvec(oH, v) for v in vecs[:12]])
+    assert relerr(y[:12], yo) < 1e-13
+    y_small = np.vstack([gpu_matvec(H, vecs[i:i + 10]) for i in range(0, 150, 10)])   # tiled kernel
+    assert relerr(y, y_small) < 1e-14
+    # a new field rebuilds the per-block entry lists (fewer surviving diagonals: Z-polarised)
+    Hz = m["pol"] * (-0.5 * AUPOL)
+    for f in ([1e9, 2e9, 3e9], [0.0, 0.0, 4e9], [1e9, 0.0, 4e9]):
+        Hz.field(f, thresh=1e2)
+        oz = oracle_of(m["pol"]).scaled(-0.5 * AUPOL)
+        oz.field(f, thresh=1e2)
+        yz = gpu_matvec(Hz, vecs)
+        assert relerr(yz[:5], np.array([port.flat_matvec(oz, v) for v in vecs[:5]])) < 1e-13
+    # fewer blocks than the window is wide
+    for jm in (1, 2, 3):
+        ms = synth.ocs(jm)
+        Hd, Hp = ms["dip"] * (-AUDIP), ms["pol"] * (-0.5 * AUPOL)
+        Hd.field(dc)
+        Hp.field(ac, thresh=1e2)
+        od, op_ = oracle_of(ms["dip"]).scaled(-AUDIP), oracle_of(ms["pol"]).scaled(-0.5 * AUPOL)
+        od.field(dc)
+        op_.field(ac, thresh=1e2)
+        vs = random_states(40, ms["h0"]._basis().N, seed=jm)
+        ys = gpu_matvec(Hd + Hp, vs)
+        osum = od.add(op_)
+        assert relerr(ys, np.array([port.flat_matvec(osum, v) for v in vs])) < 1e-13
+    # expectation through the fused epilogue of the sliding-window kernel
+    oc = oracle_of(cos2)
+    oc.field([0, 0, 1])
+    cm = oc.tomat()
+    ev = expectation(c2, vecs)
+    assert relerr(ev[:12], np.array([np.vdot(v, cm.dot(v)) for v in vecs[:12]])) < 1e-12
+    # Lanczos: fused single-launch path vs batched path with the sliding-window matvec
+    out_fused, _ = tdse.update(H, vecs, H0=h0)
+    orders_fused = tdse.last_orders.copy()
+    os.environ["RMB_FUSED"] = "0"
+    clear_device_cache()
+    try:
+        H2, _ = build()
+        t2 = TDSE(t_end=1, dt=0.01)
+        t2.time_grid()
+        out_lin, _ = t2.update(H2, vecs, H0=h0)
+        assert np.array_equal(t2.last_orders, orders_fused)
+        assert relerr(out_lin, out_fused) < 1e-12
+        ref = port.update_step(oH, vecs[:6].copy(), EXP_FAC, phase=port.h0_phase(oracle_of(h0), EXP_FAC))
+        assert relerr(out_lin[:6], ref) < TOL
+    finally:
+        del os.environ["RMB_FUSED"]
+        clear_device_cache()

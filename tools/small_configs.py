@@ -49,6 +49,20 @@ def run(name, Jmax, temp, mixed, nsteps=300, cpu_steps=10):
         H = odc.add(oac) if mixed else oac
         vc = port.update_step(H, vc, fac, phase=ph)
     dtc = time.perf_counter() - t0
+    # the same steps through the multi-step entry point (one call)
+    flds = np.array([field(i) for i in range(110, 110 + nsteps)])
+    tm = TDSE(t_end=1000, dt=0.01)
+    tm.time_grid()
+    terms = ([(Hdc, None, None)] if mixed else []) + [(Hac, flds, 1e3)]
+    vm = torch.from_numpy(vecs0).cuda()
+    tm.propagate(terms, vm, H0=h0, expect=[m["cos2"]])          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vm2, times, ev = tm.propagate(terms, vm, H0=h0, expect=[m["cos2"]])
+    torch.cuda.synchronize()
+    dtm = time.perf_counter() - t0
+    print(f"{name}: multi-step call with <cos2> every step: {nsteps/dtm:.0f} steps/s ({dtm/nsteps*1e6:.0f} us/step), "
+          f"ratio vs CPU port {nsteps/dtm/(cpu_steps/dtc):.0f}x")
     print(f"{name}: N={vecs0.shape[1]} states={len(vecs0)} orders {orders.min()}..{orders.max()}  GPU {nsteps/dt:.0f} steps/s "
           f"({len(vecs0)*nsteps/dt:.0f} state-steps/s, {dt/nsteps*1e6:.0f} us/step)  CPU port 1 core {cpu_steps/dtc:.1f} steps/s  ratio {nsteps/dt/(cpu_steps/dtc):.0f}x")
 
