@@ -390,10 +390,8 @@ def op_info(op):
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one full matvec launch from the committed ncu capture
     (profiles/), bytes per launch; None if no capture exists for this workload."""
-    if workload != "h2o":
-        return None
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")))[workload]
         return int(t["dram_bytes_read"] + t["dram_bytes_write"])
     except Exception:
         return None
