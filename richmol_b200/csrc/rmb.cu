@@ -682,7 +682,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 ebuf_elems = std::max(ebuf_elems, cap);
             }
             // T = 8 states per CTA (two groups of 4 per thread) with a ring of up to 2W+4 ket blocks (prefetch depth)
-            for (int pass = 0; pass < 6 && !op->lin_ok; ++pass) {
+            const char* ft = getenv("RMB_LIN_T");          // testing: force the 4-state tile
+            for (int pass = (ft && atoi(ft) == 4) ? 3 : 0; pass < 6 && !op->lin_ok; ++pass) {
                 const int T = pass < 3 ? 8 : 4;
                 const int NS = 2 * W + 4 - pass % 3;
                 const size_t fixed = (size_t)NS * T * dmmax * 16 + (size_t)(2 * NS + ML_NBMAX + 1) * 8 +
@@ -711,7 +712,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 if ((rc = upload(&op->d_prod_ket, h_prod_ket.data(), h_prod_ket.size()))) return rc;
                 std::vector<LinBlk> lb(d->nblocks);
                 int chunk0 = 0, ubase = 0;
-                const int G = op->lin_T / std::min(op->lin_T, ML_TS);
+                const int G = op->lin_T / (op->lin_T <= ML_TS ? op->lin_T / 2 : ML_TS);
                 for (int b = 0; b < d->nblocks; ++b) {
                     const int nch = (d->blk_dm[b] + 31) / 32;
                     lb[b].off = poff[b];

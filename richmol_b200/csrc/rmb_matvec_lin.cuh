@@ -21,7 +21,7 @@ namespace rmb {
 constexpr int ML_CWARPS = 15;                        // compute warps
 constexpr int ML_XPROD = 1;               // producer warps for the ket blocks (block j -> warp j % ML_XPROD)
 constexpr int ML_THREADS = (ML_CWARPS + ML_XPROD + 1) * 32;   // + producer warps (TMA bulk copies: ket blocks, entries)
-constexpr int ML_TS = 4;                             // states per thread
+constexpr int ML_TS = 4;                             // states per thread for the 8-state tile (T / 2 in general)
 constexpr int ML_LMAX = 40;                          // max (product, diagonal) entries per bra block
 constexpr int ML_NBMAX = 4;                          // entry buffers: 2 .. 4, as many as fit next to the ring
 
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1)
 k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict__ Y, long long ldx,
              long long ldy, int nstates, const int* __restrict__ active, const double* __restrict__ scale,
              int scale_stride, double2* __restrict__ pdot, int npart) {
-    constexpr int TS = T < ML_TS ? T : ML_TS;                 // states per thread
+    constexpr int TS = T <= ML_TS ? T / 2 : ML_TS;            // states per thread (always two state groups)
     constexpr int G = T / TS;                                 // state groups
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NS = a.NS;
@@ -235,6 +235,7 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
 
     // ================= compute warps =================
     int waited = -1;                                 // highest ket block whose arrival has been observed
+    int ws = 0, wph = 0;                             // slot / phase of the next `full` barrier to observe
     int bs = 0;                                      // b % NS
     int es = 0, eph = 0;                             // b % NB and the phase of its `efull` barrier
     const char* ring_b = reinterpret_cast<const char*>(ring);
@@ -245,16 +246,18 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
         const int nunits = ((dm1 + 31) >> 5) * G;
         int u = warp - bt.ubase;                     // first unit of the block owned by this warp
         if (u < 0) u += ML_CWARPS;
+        // Every warp observes every phase of every barrier in order, also for blocks in which it owns no unit:
+        // a parity wait is only defined for the current or the immediately preceding phase, and the waits are
+        // what keeps a warp without work from running ahead of the data (it would otherwise pass `done` for
+        // blocks the producer has not even requested and later mistake an old phase of a slot for the new one).
+        const int newest = min(b + a.W, a.nblocks - 1);
+        while (waited < newest) {
+            ++waited;
+            mbar_wait(&full[ws], (unsigned)wph);
+            if (++ws == NS) { ws = 0; wph ^= 1; }
+        }
+        mbar_wait(&efull[es], (unsigned)eph);
         if (u < nunits) {
-            // lazy waits: only the ket blocks this unit reads, b - W .. b + W, and the block's entries.  A slot is
-            // re-armed for block k + NS only after every warp (this one included) has arrived on done(k + W), so
-            // the barriers of blocks >= b - W are still in the phase waited for here, or the one just completed
-            for (int k = max(waited + 1, b - a.W); k <= min(b + a.W, a.nblocks - 1); ++k) {
-                const int q = k / NS;
-                mbar_wait(&full[k - q * NS], (unsigned)q & 1u);
-            }
-            waited = min(b + a.W, a.nblocks - 1);
-            mbar_wait(&efull[es], (unsigned)eph);
             const LinEnt* fl = flat + es * ML_FLAT;
             const double2* ev = ebuf + (size_t)es * a.ebuf_elems;
             const int L = bt.L;

@@ -622,6 +622,8 @@ def test_linear_rotor_sliding_window_kernel():
     assert relerr(y[:12], yo) < 1e-13
     y_small = np.vstack([gpu_matvec(H, vecs[i:i + 10]) for i in range(0, 150, 10)])   # tiled kernel
     assert relerr(y, y_small) < 1e-14
+    for _ in range(5):                         # the window pipeline is asynchronous: repeat
+        assert np.array_equal(gpu_matvec(H, vecs), y)
     # a new field rebuilds the per-block entry lists (fewer surviving diagonals: Z-polarised)
     Hz = m["pol"] * (-0.5 * AUPOL)
     for f in ([1e9, 2e9, 3e9], [0.0, 0.0, 4e9], [1e9, 0.0, 4e9]):
@@ -643,6 +645,16 @@ def test_linear_rotor_sliding_window_kernel():
         ys = gpu_matvec(Hd + Hp, vs)
         osum = od.add(op_)
         assert relerr(ys, np.array([port.flat_matvec(osum, v) for v in vs])) < 1e-13
+    # the 4-state tile used when the ring of an 8-state tile does not fit (large Jmax)
+    os.environ["RMB_LIN_T"] = "4"
+    clear_device_cache()
+    try:
+        H4, _ = build()
+        for _ in range(3):
+            assert relerr(gpu_matvec(H4, vecs), y) < 1e-14
+    finally:
+        del os.environ["RMB_LIN_T"]
+        clear_device_cache()
     # expectation through the fused epilogue of the sliding-window kernel
     oc = oracle_of(cos2)
     oc.field([0, 0, 1])
