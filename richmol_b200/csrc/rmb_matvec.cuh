@@ -248,9 +248,14 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
             if (xbytes > 0 && sb >= 0)
                 tma_load_1d(sm.xbuf[stage] + (long long)lane * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
                             &sm.full[stage]);
-            if (lane < nnz)
+            if (it.nrows == it.dm1) {
+                // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
+                if (lane == 0 && nnz > 0)
+                    tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
+            } else if (lane < nnz) {
                 tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
                             mbytes, &sm.full[stage]);
+            }
         }
     } else {
         // ================= consumer warps =================
