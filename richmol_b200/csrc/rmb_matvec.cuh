@@ -15,7 +15,8 @@
 namespace rmb {
 
 constexpr int MV2_CONSUMERS = 128;               // compute threads: one row of TWO states each
-constexpr int MV2_THREADS = MV2_CONSUMERS + 32;  // + one producer warp issuing the TMA bulk copies
+constexpr int MV2_PRODUCERS = 2;                 // producer warps issuing the TMA bulk copies (states split even / odd)
+constexpr int MV2_THREADS = MV2_CONSUMERS + 32 * MV2_PRODUCERS;
 constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
 constexpr int MV2_SMAX = 32;      // max states per CTA
@@ -162,7 +163,7 @@ struct Mv2Smem {
 //    registers; per block product p it forms z = sum_q MF_p[m1, q] * X[row_q, k2] on the fly (only the
 //    diagonals that survived the field contraction) and accumulates acc[k1] += K_p[k1, k2] * z with
 //    K_p^T broadcast from shared memory.  H(t) itself is never materialised.
-//  * 1 producer warp: stages, per product and two products ahead of use, the ket rows of every state of
+//  * 2 producer warps (states split even / odd): stage, per product and two products ahead of use, the ket rows of every state of
 //    the tile and the MF diagonals with TMA bulk copies (cp.async.bulk) completing on an mbarrier; the
 //    internal vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous,
 //    bank-conflict-free run.
@@ -189,7 +190,7 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < MV2_STAGES; ++i) {
-            mbar_init(&sm.full[i], 1);                       // producer lane 0 (arrive.expect_tx) + tx bytes
+            mbar_init(&sm.full[i], MV2_PRODUCERS);           // lane 0 of every producer warp (arrive.expect_tx) + tx bytes
             mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
         }
         mbar_init(sm.setup, 1 + 32);                         // expect_tx arrival + every producer lane
@@ -203,50 +204,49 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
 
     if (producer) {
         // ================= producer warp: TMA bulk copies, MV2_STAGES products ahead =================
-        const int lane = threadIdx.x - MV2_CONSUMERS;
-        // the K^T image of all products and the static descriptors were laid out on the host exactly as
-        // they sit in shared memory: two bulk copies
-        if (lane == 0) {
-            const unsigned kbytes = (unsigned)it.kt_total * 8u, dbytes = (unsigned)np * (unsigned)sizeof(ProdS);
-            mbar_arrive_expect_tx(sm.setup, kbytes + dbytes);
-            if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
-            if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
+        const int pw = (threadIdx.x - MV2_CONSUMERS) >> 5;    // producer warp: copies the states s % MV2_PRODUCERS == pw
+        const int lane = threadIdx.x & 31;
+        const int* snnz = reinterpret_cast<const int*>(sm.setup + 1);
+        if (pw == 0) {
+            // the K^T image of all products and the static descriptors were laid out on the host exactly as
+            // they sit in shared memory: two bulk copies
+            if (lane == 0) {
+                const unsigned kbytes = (unsigned)it.kt_total * 8u, dbytes = (unsigned)np * (unsigned)sizeof(ProdS);
+                mbar_arrive_expect_tx(sm.setup, kbytes + dbytes);
+                if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
+                if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
+            }
+            // diagonals that survived the field contraction (field-dependent: read from the masks).  nnz goes to
+            // its own shared array (the descriptors are still in flight); the setup barrier completes when the
+            // bulk copies have landed and every lane of this warp has published its values
+            int* wnnz = reinterpret_cast<int*>(sm.setup + 1);
+    #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ip = lane + 32 * j;
+                if (ip < np) wnnz[ip] = min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX);
+            }
+            mbar_arrive(sm.setup);                           // release: snnz visible to whoever waits
         }
-        // state offsets of this tile (one lane per state)
+        // state offset handled by this lane
         long long sb = -1;
-        if (lane < it.nst) {
-            const int s = s0 + lane;
+        const int sidx = lane * MV2_PRODUCERS + pw;
+        if (sidx < it.nst) {
+            const int s = s0 + sidx;
             if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
         }
         const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
-        // diagonals that survived the field contraction (field-dependent: read from the masks)
-        int my_nnz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ip = lane + 32 * j;
-            my_nnz[j] = ip < np ? min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX) : 0;
-        }
-        // nnz goes to its own shared array (the descriptors are still in flight); the setup barrier
-        // completes when the bulk copies have landed and every producer lane has published its values
-        int* snnz = reinterpret_cast<int*>(sm.setup + 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ip = lane + 32 * j;
-            if (ip < np) snnz[ip] = my_nnz[j];
-        }
-        mbar_arrive(sm.setup);                               // release: snnz visible to whoever waits
         mbar_wait(sm.setup, 0);
         for (int ip = 0; ip < np; ++ip) {
             const int stage = ip % MV2_STAGES;
             if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
             const ProdS d = sm.sp[ip];
-            const int nnz = snnz[ip];
+            const int nnz = pw == 0 ? snnz[ip] : 0;          // warp 0 also brings the MF diagonals
             const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
             const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
             if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
             __syncwarp();
             if (xbytes > 0 && sb >= 0)
-                tma_load_1d(sm.xbuf[stage] + (long long)lane * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
+                tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
                             &sm.full[stage]);
             if (it.nrows == it.dm1) {
                 // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
