@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librichmol_b200.so")
+LIB_PATH = os.environ.get("RMB_LIB") or os.path.join(_HERE, "librichmol_b200.so")   # RMB_LIB: A/B builds (tools/)
 
 RMB_OK, RMB_ERR_INVALID, RMB_ERR_CUDA, RMB_ERR_MAXORDER, RMB_ERR_NOFIELD = 0, -1, -2, -3, -4
 

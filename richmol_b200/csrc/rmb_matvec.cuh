@@ -15,8 +15,13 @@
 namespace rmb {
 
 constexpr int MV2_CONSUMERS = 128;               // compute threads: one row of TWO states each
-constexpr int MV2_PRODUCERS = 2;                 // producer warps issuing the TMA bulk copies (states split even / odd)
-constexpr int MV2_THREADS = MV2_CONSUMERS + 32 * MV2_PRODUCERS;
+constexpr int MV2_PRODUCERS = 4;                 // producer warps issuing the TMA bulk copies (state s -> warp s % 4)
+constexpr int MV2_THREADS = MV2_CONSUMERS + 32 * MV2_PRODUCERS;   // two warpgroups: consumers, producers
+// Register split between the warpgroups (setmaxnreg): the CTA is launched with 128 registers per thread
+// (256 threads, two CTAs per SM); the producers keep 40 and the consumers grow to 208, which holds the
+// 2 x 12 complex accumulators, a K^T row and both sets of ket elements without spilling.
+constexpr int MV2_REGS_PRODUCER = 40;
+constexpr int MV2_REGS_CONSUMER = 208;
 constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
 constexpr int MV2_SMAX = 32;      // max states per CTA
@@ -78,77 +83,141 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// dynamic shared memory of the matvec kernels.  Staged data is addressed as `rmb_dsmem + byte offset` so that the
+// compiler sees the shared address space (LDS instead of generic loads).
+extern __shared__ __align__(128) unsigned char rmb_dsmem[];
+
+#ifndef RMB_MV2_PREFETCH_K
+#define RMB_MV2_PREFETCH_K 1      // K^T rows one k2 ahead in registers when they fit (the ket elements: see PX)
+#endif
+#ifndef RMB_MV2_REGS
+#define RMB_MV2_REGS 180          // registers the inner loop may plan with (the rest: addresses, loop state)
+#endif
+
+// acc[k1] += K[k1,k2] * z for the two states of a thread; `krow` is row k2 of the K^T image in registers
+template <int NC, bool KC>
+__device__ __forceinline__ void mv2_kstage(const double (&krow)[KC ? 2 * NC : NC], const double2& zA, const double2& zB,
+                                           double2 (&accA)[NC], double2 (&accB)[NC]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (KC) {
+            const double kx = krow[2 * c], ky = krow[2 * c + 1];
+            accA[c].x = fma(kx, zA.x, accA[c].x);
+            accA[c].y = fma(kx, zA.y, accA[c].y);
+            accB[c].x = fma(kx, zB.x, accB[c].x);
+            accB[c].y = fma(kx, zB.y, accB[c].y);
+            accA[c].x = fma(-ky, zA.y, accA[c].x);
+            accA[c].y = fma(ky, zA.x, accA[c].y);
+            accB[c].x = fma(-ky, zB.y, accB[c].x);
+            accB[c].y = fma(ky, zB.x, accB[c].y);
+        } else {
+            const double kv = krow[c];
+            accA[c].x = fma(kv, zA.x, accA[c].x);
+            accA[c].y = fma(kv, zA.y, accA[c].y);
+            accB[c].x = fma(kv, zB.x, accB[c].x);
+            accB[c].y = fma(kv, zB.y, accB[c].y);
+        }
+    }
+}
+
+// row k2 of the K^T image ([k2][NC] doubles, or [k2][NC] double2 for complex K) -> registers
+template <int NC, bool KC>
+__device__ __forceinline__ void mv2_load_krow(unsigned kt_byte, int k2, double (&krow)[KC ? 2 * NC : NC]) {
+    constexpr int ND = KC ? 2 * NC : NC;
+    if (ND == 1) {
+        krow[0] = *reinterpret_cast<const double*>(rmb_dsmem + kt_byte + (unsigned)k2 * 8u);
+    } else {
+        const double2* src = reinterpret_cast<const double2*>(rmb_dsmem + kt_byte + (unsigned)(k2 * ND) * 8u);
+#pragma unroll
+        for (int c = 0; c < ND / 2; ++c) {
+            const double2 v = src[c];
+            krow[2 * c] = v.x;
+            krow[2 * c + 1] = v.y;
+        }
+    }
+}
+
 // one block product for one thread (one row m1 of two states A, B):
 //   acc[k1] += sum_k2 K[k1,k2] * (sum_q MF[q] * X[row_q, k2])
-// K^T values are loaded once per k2 and used for both states (halves the shared-memory traffic per DFMA)
+// K^T values are loaded once per k2 and used for both states (halves the shared-memory traffic per DFMA).
+// Software pipeline over k2: the ket elements of column k2 + 1 (and, for few diagonals, row k2 + 1 of K^T) are
+// loaded into a second register set before the DFMAs of column k2, so the LDS latency of one column hides behind
+// the 4 * NC + 8 * NNZ DFMAs of the previous one (two consumer warps per scheduler are not enough to hide it).
 template <int NC, int NNZ, bool KC>
-__device__ __forceinline__ void mv2_inner(const double2* __restrict__ xa, const double2* __restrict__ xb,
-                                          const MfEntry* __restrict__ mfe, int nrows, int c_lo, int xrs,
-                                          const double* __restrict__ ktp, int dk2, double2 (&accA)[NC],
-                                          double2 (&accB)[NC]) {
+__device__ __forceinline__ void mv2_inner(unsigned xa_byte, unsigned xb_byte, unsigned mfe_byte,
+                                          int nrows, int c_lo, int xrs, unsigned kt_byte, int dk2,
+                                          double2 (&accA)[NC], double2 (&accB)[NC]) {
+    constexpr int ND = KC ? 2 * NC : NC;
+    // register budget (168 per thread at two CTAs of 192 threads per SM): accumulators 8 NC, a K^T row 2 ND,
+    // ket elements, MF values and offsets 13 NNZ (+ 8 NNZ for the second set)
+    constexpr bool PK = RMB_MV2_PREFETCH_K && 8 * NC + 4 * ND + 21 * NNZ <= RMB_MV2_REGS;
+    constexpr bool PX = 8 * NC + (PK ? 4 : 2) * ND + 21 * NNZ <= RMB_MV2_REGS;
     double2 mf[NNZ];
-    int xo[NNZ];
+    unsigned xo[NNZ];
 #pragma unroll
     for (int q = 0; q < NNZ; ++q) {
-        const MfEntry e = mfe[q * nrows];
-        mf[q] = make_double2(e.re, e.im);
-        xo[q] = e.col >= 0 ? (e.col - c_lo) * xrs : 0;      // value is 0 when the diagonal leaves the block
+        const unsigned char* ep = rmb_dsmem + mfe_byte + (unsigned)(q * nrows) * (unsigned)sizeof(MfEntry);
+        mf[q] = *reinterpret_cast<const double2*>(ep);
+        const int col = *reinterpret_cast<const int*>(ep + 16);
+        xo[q] = col >= 0 ? (unsigned)((col - c_lo) * xrs) * 16u : 0u;   // value is 0 when the diagonal leaves the block
     }
+    double2 a[NNZ], b[NNZ];
+    double krow[ND];
+#pragma unroll
+    for (int q = 0; q < NNZ; ++q) {
+        a[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xa_byte + xo[q]);
+        b[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xb_byte + xo[q]);
+    }
+    if (PK) mv2_load_krow<NC, KC>(kt_byte, 0, krow);
 #pragma unroll 2
     for (int k2 = 0; k2 < dk2; ++k2) {
+        const int kn = min(k2 + 1, dk2 - 1);                 // the last column re-loads itself (no branch)
+        double2 an[NNZ], bn[NNZ];
+        double krown[ND];
+        if (!PK) mv2_load_krow<NC, KC>(kt_byte, k2, krow);
+        if (PX) {
+#pragma unroll
+            for (int q = 0; q < NNZ; ++q) {
+                an[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xa_byte + xo[q] + (unsigned)kn * 16u);
+                bn[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xb_byte + xo[q] + (unsigned)kn * 16u);
+            }
+        }
+        if (PK) mv2_load_krow<NC, KC>(kt_byte, kn, krown);
         double2 zA = make_double2(0.0, 0.0), zB = make_double2(0.0, 0.0);
 #pragma unroll
         for (int q = 0; q < NNZ; ++q) {
-            const double2 a = xa[xo[q] + k2], b = xb[xo[q] + k2];
-            zA.x = fma(mf[q].x, a.x, zA.x);
-            zA.y = fma(mf[q].x, a.y, zA.y);
-            zB.x = fma(mf[q].x, b.x, zB.x);
-            zB.y = fma(mf[q].x, b.y, zB.y);
-            zA.x = fma(-mf[q].y, a.y, zA.x);
-            zA.y = fma(mf[q].y, a.x, zA.y);
-            zB.x = fma(-mf[q].y, b.y, zB.x);
-            zB.y = fma(mf[q].y, b.x, zB.y);
+            zA.x = fma(mf[q].x, a[q].x, zA.x);
+            zA.y = fma(mf[q].x, a[q].y, zA.y);
+            zB.x = fma(mf[q].x, b[q].x, zB.x);
+            zB.y = fma(mf[q].x, b[q].y, zB.y);
+            zA.x = fma(-mf[q].y, a[q].y, zA.x);
+            zA.y = fma(mf[q].y, a[q].x, zA.y);
+            zB.x = fma(-mf[q].y, b[q].y, zB.x);
+            zB.y = fma(mf[q].y, b[q].x, zB.y);
         }
-        if (KC) {
-            const double2* krow = reinterpret_cast<const double2*>(ktp) + k2 * NC;
+        mv2_kstage<NC, KC>(krow, zA, zB, accA, accB);
+        if (PX) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const double2 kv = krow[c];
-                accA[c].x = fma(kv.x, zA.x, accA[c].x);
-                accA[c].y = fma(kv.x, zA.y, accA[c].y);
-                accB[c].x = fma(kv.x, zB.x, accB[c].x);
-                accB[c].y = fma(kv.x, zB.y, accB[c].y);
-                accA[c].x = fma(-kv.y, zA.y, accA[c].x);
-                accA[c].y = fma(kv.y, zA.x, accA[c].y);
-                accB[c].x = fma(-kv.y, zB.y, accB[c].x);
-                accB[c].y = fma(kv.y, zB.x, accB[c].y);
-            }
-        } else if (NC == 1) {
-            const double kv = ktp[k2];
-            accA[0].x = fma(kv, zA.x, accA[0].x);
-            accA[0].y = fma(kv, zA.y, accA[0].y);
-            accB[0].x = fma(kv, zB.x, accB[0].x);
-            accB[0].y = fma(kv, zB.y, accB[0].y);
+            for (int q = 0; q < NNZ; ++q) { a[q] = an[q]; b[q] = bn[q]; }
         } else {
-            const double2* krow = reinterpret_cast<const double2*>(ktp + k2 * NC);
 #pragma unroll
-            for (int c2 = 0; c2 < NC / 2; ++c2) {
-                const double2 kv = krow[c2];
-                accA[2 * c2].x = fma(kv.x, zA.x, accA[2 * c2].x);
-                accA[2 * c2].y = fma(kv.x, zA.y, accA[2 * c2].y);
-                accB[2 * c2].x = fma(kv.x, zB.x, accB[2 * c2].x);
-                accB[2 * c2].y = fma(kv.x, zB.y, accB[2 * c2].y);
-                accA[2 * c2 + 1].x = fma(kv.y, zA.x, accA[2 * c2 + 1].x);
-                accA[2 * c2 + 1].y = fma(kv.y, zA.y, accA[2 * c2 + 1].y);
-                accB[2 * c2 + 1].x = fma(kv.y, zB.x, accB[2 * c2 + 1].x);
-                accB[2 * c2 + 1].y = fma(kv.y, zB.y, accB[2 * c2 + 1].y);
+            for (int q = 0; q < NNZ; ++q) {
+                a[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xa_byte + xo[q] + (unsigned)kn * 16u);
+                b[q] = *reinterpret_cast<const double2*>(rmb_dsmem + xb_byte + xo[q] + (unsigned)kn * 16u);
             }
+        }
+        if (PK) {
+#pragma unroll
+            for (int c = 0; c < ND; ++c) krow[c] = krown[c];
         }
     }
 }
 
 struct Mv2Smem {
     double2* xbuf[MV2_STAGES];
+    unsigned xbuf_b[MV2_STAGES]; // the same as byte offsets into rmb_dsmem
+    unsigned mfe_b[MV2_STAGES];
+    unsigned kt_b, sp_b, snnz_b;
     MfEntry* mfe[MV2_STAGES];
     double* kt;
     ProdS* sp;
@@ -168,123 +237,46 @@ struct Mv2Smem {
 //    internal vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous,
 //    bank-conflict-free run.
 template <int NC, bool KC>
-__device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restrict__ gdesc,
-                                         const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
-                                         const double* __restrict__ ktpool, const double2* __restrict__ X,
-                                         double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
-                                         int s0, const int* __restrict__ active, const Mv2Smem& sm,
-                                         const double* __restrict__ scale, int scale_stride,
-                                         double2* __restrict__ pdot, int npart, int item_index) {
+__device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __restrict__ X,
+                                             double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
+                                             int s0, const int* __restrict__ active, const Mv2Smem& sm,
+                                             const double* __restrict__ scale, int scale_stride,
+                                             double2* __restrict__ pdot, int npart, int item_index,
+                                             int sl, int rl, bool inb, bool vA, bool vB) {
     constexpr int KW = KC ? 2 : 1;                       // doubles per K element
-    const bool producer = threadIdx.x >= MV2_CONSUMERS;
-    const int sl = threadIdx.x / it.nrows;               // state pair of this thread
-    const int rl = threadIdx.x - sl * it.nrows;
     const int stA = s0 + 2 * sl, stB = stA + 1;
-    const bool inb = !producer && 2 * sl < it.nst;
-    const bool vA = inb && stA < nstates && (active == nullptr || active[stA]);
-    const bool vB = inb && stB < nstates && (active == nullptr || active[stB]);
     const bool work = vA || vB;
     const int np = it.p_end - it.p_begin;
-    if (__syncthreads_or(work) == 0) return;             // every state of the tile has converged
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < MV2_STAGES; ++i) {
-            mbar_init(&sm.full[i], MV2_PRODUCERS);           // lane 0 of every producer warp (arrive.expect_tx) + tx bytes
-            mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
-        }
-        mbar_init(sm.setup, 1 + 32);                         // expect_tx arrival + every producer lane
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-
     double2 accA[NC], accB[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
 
-    if (producer) {
-        // ================= producer warp: TMA bulk copies, MV2_STAGES products ahead =================
-        const int pw = (threadIdx.x - MV2_CONSUMERS) >> 5;    // producer warp: copies the states s % MV2_PRODUCERS == pw
-        const int lane = threadIdx.x & 31;
-        const int* snnz = reinterpret_cast<const int*>(sm.setup + 1);
-        if (pw == 0) {
-            // the K^T image of all products and the static descriptors were laid out on the host exactly as
-            // they sit in shared memory: two bulk copies
-            if (lane == 0) {
-                const unsigned kbytes = (unsigned)it.kt_total * 8u, dbytes = (unsigned)np * (unsigned)sizeof(ProdS);
-                mbar_arrive_expect_tx(sm.setup, kbytes + dbytes);
-                if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
-                if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
-            }
-            // diagonals that survived the field contraction (field-dependent: read from the masks).  nnz goes to
-            // its own shared array (the descriptors are still in flight); the setup barrier completes when the
-            // bulk copies have landed and every lane of this warp has published its values
-            int* wnnz = reinterpret_cast<int*>(sm.setup + 1);
-    #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ip = lane + 32 * j;
-                if (ip < np) wnnz[ip] = min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX);
-            }
-            mbar_arrive(sm.setup);                           // release: snnz visible to whoever waits
-        }
-        // state offset handled by this lane
-        long long sb = -1;
-        const int sidx = lane * MV2_PRODUCERS + pw;
-        if (sidx < it.nst) {
-            const int s = s0 + sidx;
-            if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
-        }
-        const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
-        mbar_wait(sm.setup, 0);
-        for (int ip = 0; ip < np; ++ip) {
-            const int stage = ip % MV2_STAGES;
-            if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
-            const ProdS d = sm.sp[ip];
-            const int nnz = pw == 0 ? snnz[ip] : 0;          // warp 0 also brings the MF diagonals
-            const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
-            const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
-            __syncwarp();
-            if (xbytes > 0 && sb >= 0)
-                tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
-                            &sm.full[stage]);
-            if (it.nrows == it.dm1) {
-                // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
-                if (lane == 0 && nnz > 0)
-                    tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
-            } else if (lane < nnz) {
-                tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
-                            mbytes, &sm.full[stage]);
+    const int* snnz = reinterpret_cast<const int*>(rmb_dsmem + sm.snnz_b);
+    const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
+    mbar_wait(sm.setup, 0);
+    int ktbase = 0;
+    for (int ip = 0; ip < np; ++ip) {
+        const int stage = ip % MV2_STAGES;
+        mbar_wait(&sm.full[stage], (ip / MV2_STAGES) & 1);
+        const int dk2 = sp[ip].dk2, nnz = snnz[ip];
+        if (work) {
+            const int nr = sp[ip].nr, xrs = sp[ip].xrs, c_lo = sp[ip].c_lo;
+            const unsigned xa = sm.xbuf_b[stage] + (unsigned)((2 * sl) * nr * xrs) * 16u;
+            const unsigned xb = xa + (unsigned)(nr * xrs) * 16u;   // an inactive partner reads stale data: never stored
+            const unsigned mfe = sm.mfe_b[stage] + (unsigned)rl * (unsigned)sizeof(MfEntry);
+            const unsigned ktp = sm.kt_b + (unsigned)ktbase * 8u;
+            switch (nnz) {
+                case 0: break;
+                case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                default: mv2_inner<NC, 5, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
             }
         }
-    } else {
-        // ================= consumer warps =================
-        const int* snnz = reinterpret_cast<const int*>(sm.setup + 1);
-        mbar_wait(sm.setup, 0);
-        int ktbase = 0;
-        for (int ip = 0; ip < np; ++ip) {
-            const int stage = ip % MV2_STAGES;
-            mbar_wait(&sm.full[stage], (ip / MV2_STAGES) & 1);
-            const int dk2 = sm.sp[ip].dk2, nnz = snnz[ip];
-            if (work) {
-                const int nr = sm.sp[ip].nr, xrs = sm.sp[ip].xrs, c_lo = sm.sp[ip].c_lo;
-                const double2* xa = sm.xbuf[stage] + (long long)(2 * sl) * nr * xrs;
-                const double2* xb = xa + (long long)nr * xrs;   // an inactive partner reads stale data: never stored
-                const MfEntry* mfe = sm.mfe[stage] + rl;
-                const double* ktp = sm.kt + ktbase;
-                switch (nnz) {
-                    case 0: break;
-                    case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    default: mv2_inner<NC, 5, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                }
-            }
-            ktbase += dk2 * NC * KW;
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
-        }
+        ktbase += dk2 * NC * KW;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
     }
     // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
     //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
@@ -316,8 +308,10 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
     if (vA) finish(accA, stA, preA, pimA);
     if (vB) finish(accB, stB, preB, pimB);
     if (pdot != nullptr) {
-        __syncthreads();                        // all stages consumed: the staging buffers are free
-        double* red = reinterpret_cast<double*>(sm.xbuf[0]);   // [2][nst][nrows]
+        // consumer warps only (the producers have left): named barrier 1.  Every consumer has passed the last
+        // `full` wait, so all stages are consumed and the staging buffers are free
+        asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
+        double* red = reinterpret_cast<double*>(rmb_dsmem + sm.xbuf_b[0]);   // [2][nst][nrows]
         const int half = it.nst * it.nrows;
         if (inb) {
             red[(2 * sl) * it.nrows + rl] = preA;
@@ -325,9 +319,9 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
             red[half + (2 * sl) * it.nrows + rl] = pimA;
             red[half + (2 * sl + 1) * it.nrows + rl] = pimB;
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int s = warp; s < it.nst; s += MV2_THREADS / 32) {
+        for (int s = warp; s < it.nst; s += MV2_CONSUMERS / 32) {
             const int sg = s0 + s;
             if (sg >= nstates || (active != nullptr && !active[sg])) continue;
             double a = 0.0, b = 0.0;
@@ -345,6 +339,68 @@ __device__ __forceinline__ void mv2_body(const Item2D& it, const ProdS* __restri
     }
 }
 
+// producer warpgroup: TMA bulk copies, MV2_STAGES products ahead of the consumers
+__device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __restrict__ gdesc,
+                                             const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
+                                             const double* __restrict__ ktpool, const double2* __restrict__ X,
+                                             long long ldx, int nstates, int s0, const int* __restrict__ active,
+                                             const Mv2Smem& sm) {
+    const int np = it.p_end - it.p_begin;
+    const int pw = (threadIdx.x - MV2_CONSUMERS) >> 5;    // producer warp: copies the states s % MV2_PRODUCERS == pw
+    const int lane = threadIdx.x & 31;
+    int* wnnz = reinterpret_cast<int*>(rmb_dsmem + sm.snnz_b);
+    const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
+    if (pw == 0) {
+        // the K^T image of all products and the static descriptors were laid out on the host exactly as
+        // they sit in shared memory: two bulk copies
+        if (lane == 0) {
+            const unsigned kbytes = (unsigned)it.kt_total * 8u, dbytes = (unsigned)np * (unsigned)sizeof(ProdS);
+            mbar_arrive_expect_tx(sm.setup, kbytes + dbytes);
+            if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
+            if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
+        }
+        // diagonals that survived the field contraction (field-dependent: read from the masks).  nnz goes to
+        // its own shared array (the descriptors are still in flight); the setup barrier completes when the
+        // bulk copies have landed and every lane of this warp has published its values
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ip = lane + 32 * j;
+            if (ip < np) wnnz[ip] = min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX);
+        }
+        mbar_arrive(sm.setup);                           // release: snnz visible to whoever waits
+    }
+    // state offset handled by this lane
+    long long sb = -1;
+    const int sidx = lane * MV2_PRODUCERS + pw;
+    if (sidx < it.nst) {
+        const int s = s0 + sidx;
+        if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
+    }
+    const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
+    mbar_wait(sm.setup, 0);
+    for (int ip = 0; ip < np; ++ip) {
+        const int stage = ip % MV2_STAGES;
+        if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
+        const ProdS d = sp[ip];
+        const int nnz = pw == 0 ? wnnz[ip] : 0;          // warp 0 also brings the MF diagonals
+        const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
+        const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
+        if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
+        __syncwarp();
+        if (xbytes > 0 && sb >= 0)
+            tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
+                        &sm.full[stage]);
+        if (it.nrows == it.dm1) {
+            // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
+            if (lane == 0 && nnz > 0)
+                tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
+        } else if (lane < nnz) {
+            tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
+                        mbytes, &sm.full[stage]);
+        }
+    }
+}
+
 template <bool KC>
 __global__ void __launch_bounds__(MV2_THREADS, 2)
 k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ items,
@@ -353,24 +409,60 @@ k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ item
                const double2* __restrict__ X, double2* __restrict__ Y, long long ldx, long long ldy,
                int nstates, const int* __restrict__ active, const double* __restrict__ scale,
                int scale_stride, double2* __restrict__ pdot, int npart) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* const smem_raw = rmb_dsmem;
     const Unit2D u = units[blockIdx.x];
     const Item2D it = items[u.item];
     const int np = it.p_end - it.p_begin;
     // shared memory is carved with the sizes of this item (the launch reserves the maximum over items)
     Mv2Smem sm;
     unsigned char* p = smem_raw;
-    for (int i = 0; i < MV2_STAGES; ++i) { sm.xbuf[i] = reinterpret_cast<double2*>(p); p += (size_t)it.xbuf_elems * 16; }
-    for (int i = 0; i < MV2_STAGES; ++i) { sm.mfe[i] = reinterpret_cast<MfEntry*>(p); p += (size_t)MV2_NDMAX * it.nrows * sizeof(MfEntry); }
-    sm.kt = reinterpret_cast<double*>(p); p += (size_t)it.kt_total * 8;
-    sm.sp = reinterpret_cast<ProdS*>(p); p += (size_t)np * sizeof(ProdS);
+    for (int i = 0; i < MV2_STAGES; ++i) {
+        sm.xbuf[i] = reinterpret_cast<double2*>(p);
+        sm.xbuf_b[i] = (unsigned)(p - smem_raw);
+        p += (size_t)it.xbuf_elems * 16;
+    }
+    for (int i = 0; i < MV2_STAGES; ++i) {
+        sm.mfe[i] = reinterpret_cast<MfEntry*>(p);
+        sm.mfe_b[i] = (unsigned)(p - smem_raw);
+        p += (size_t)MV2_NDMAX * it.nrows * sizeof(MfEntry);
+    }
+    sm.kt = reinterpret_cast<double*>(p); sm.kt_b = (unsigned)(p - smem_raw); p += (size_t)it.kt_total * 8;
+    sm.sp = reinterpret_cast<ProdS*>(p); sm.sp_b = (unsigned)(p - smem_raw); p += (size_t)np * sizeof(ProdS);
     sm.full = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
     sm.empty = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
     sm.setup = reinterpret_cast<unsigned long long*>(p);     // followed by int snnz[np]
+    sm.snnz_b = (unsigned)(p + 8 - smem_raw);
+
+    const bool producer = threadIdx.x >= MV2_CONSUMERS;
+    const int sl = threadIdx.x / it.nrows;               // state pair of this thread
+    const int rl = threadIdx.x - sl * it.nrows;
+    const int stA = u.s0 + 2 * sl, stB = stA + 1;
+    const bool inb = !producer && 2 * sl < it.nst;
+    const bool vA = inb && stA < nstates && (active == nullptr || active[stA]);
+    const bool vB = inb && stB < nstates && (active == nullptr || active[stB]);
+    if (__syncthreads_or(vA || vB) == 0) return;         // every state of the tile has converged
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MV2_STAGES; ++i) {
+            mbar_init(&sm.full[i], MV2_PRODUCERS);           // lane 0 of every producer warp (arrive.expect_tx) + tx bytes
+            mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
+        }
+        mbar_init(sm.setup, 1 + 32);                         // expect_tx arrival + every lane of producer warp 0
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(MV2_REGS_PRODUCER));
+        mv2_producer(it, gdesc, cent, tab_mask, ktpool, X, ldx, nstates, u.s0, active, sm);
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(MV2_REGS_CONSUMER));
 #define RMB_CASE(N)                                                                                        \
     case N:                                                                                                \
-        mv2_body<N, KC>(it, gdesc, cent, tab_mask, ktpool, X, Y, ldx, ldy, nstates,                        \
-                        u.s0, active, sm, scale, scale_stride, pdot, npart, u.item);                       \
+        mv2_consumer<N, KC>(it, X, Y, ldx, ldy, nstates, u.s0, active, sm, scale, scale_stride, pdot,      \
+                            npart, u.item, sl, rl, inb, vA, vB);                                           \
         break;
     switch (it.nc == 1 ? 1 : (it.nc + 1) & ~1) {
         RMB_CASE(1) RMB_CASE(2) RMB_CASE(4) RMB_CASE(6) RMB_CASE(8)
