@@ -333,7 +333,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     }
     auto item_smem = [](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod) {
         return (size_t)MV2_STAGES * xbuf_elems * 16 + (size_t)MV2_STAGES * MV2_NDMAX * nrows * sizeof(MfEntry) +
-               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (2 * MV2_STAGES + 1) * 8 + (size_t)nprod * 4 + 128;
+               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (2 * MV2_STAGES + 1) * 8 + (size_t)nprod * 4 + 16 +
+               MV2_RED_BYTES + 128;
     };
     const char* force = getenv("RMB_MATVEC");
     auto itemG_smem = [](size_t xbuf_elems, int nrows, int ldk) {
@@ -350,7 +351,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     std::vector<ProdS> gdesc;                 // static per-(item, product) descriptors, shared-memory layout
     std::vector<double> ktpool;               // K^T images per (bra block, column chunk), shared-memory layout
     std::map<std::pair<int, int>, long long> kt_index;
-    const size_t smem_budget = 108 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
+    const size_t smem_budget = 112 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
     for (int b = 0; b < d->nblocks; ++b) {
         const int dk1 = d->blk_dk[b], dm1 = d->blk_dm[b];
         if (dk1 == 0 || dm1 == 0) continue;
@@ -613,6 +614,13 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     for (auto& it : itemsG) op->h_itemG_states.push_back(it.nst);
     op->nitems2 = (int)items2.size();
     for (auto& it : items2) op->h_item2_states.push_back(it.nst);
+    if (getenv("RMB_DEBUG")) {
+        fprintf(stderr, "[rmb] tiled items %d (smem %zu B), DMMA items %d (smem %zu B), scalar items %zu\n",
+                op->nitems2, op->matvec2_smem, op->nitemsG, op->matvecG_smem, op->h_items.size());
+        for (auto& it : items2)
+            fprintf(stderr, "[rmb]   item dm1 %d dk1 %d rows %d nc %d nst %d products %d xbuf %d B kt %d B\n", it.dm1,
+                    it.dk1, it.nrows, it.nc, it.nst, it.p_end - it.p_begin, it.xbuf_elems * 16, it.kt_total * 8);
+    }
 
     opbytes += 20.0 * (double)op->nent;   // MF values + column indices
     op->flops_per_state = flops;
@@ -750,6 +758,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         }
     }
     if ((rc = upload((ProdS**)&op->d_gdesc, gdesc.data(), gdesc.size()))) return rc;
+    op->ngdesc = (int)gdesc.size();
     ktpool.push_back(0.0);
     ktpool.push_back(0.0);
     if ((rc = upload(&op->d_ktpool, ktpool.data(), ktpool.size()))) return rc;
@@ -828,6 +837,7 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
         op->n_launches += 2;
         op->lin_flat_dirty = true;
     }
+    op->nnz_dirty = true;
     ph.has_field = true;
     {
         unsigned nz = 0;
@@ -945,9 +955,19 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
     if (op->nitems2 > 0) {
         // work units (item, first state) for this batch size; rebuilt only when the size changes
         if (op->units_nstates != nstates) {
+            // a CTA walks `tiles` consecutive state tiles of one item (K^T image, descriptors and pipeline set up
+            // once); fewer, longer CTAs as long as the grid still fills the 2 x 148 CTA slots several times over
             std::vector<Unit2D> units;
-            for (int i = 0; i < op->nitems2; ++i)
-                for (long long s0 = 0; s0 < nstates; s0 += op->h_item2_states[i]) units.push_back({i, (int)s0});
+            long long ntile_total = 0;
+            for (int i = 0; i < op->nitems2; ++i) ntile_total += (nstates + op->h_item2_states[i] - 1) / op->h_item2_states[i];
+            int tiles = (int)std::max<long long>(1, std::min<long long>(MV2_TILES_MAX, ntile_total / (6 * 2 * 148)));
+            if (const char* e = getenv("RMB_MV2_TILES")) tiles = std::max(1, std::min(MV2_TILES_MAX, atoi(e)));
+            for (int i = 0; i < op->nitems2; ++i) {
+                const long long nst = op->h_item2_states[i];
+                const int tl = (int)std::min<long long>(tiles, std::max<long long>(1, 256 / nst));   // one flag thread per state
+                for (long long s0 = 0; s0 < nstates; s0 += nst * tl)
+                    units.push_back({i, (int)s0, (int)std::min<long long>(tl, (nstates - s0 + nst - 1) / nst), 0});
+            }
             if ((int)units.size() > op->units_cap) {
                 RMB_CUDA(cudaStreamSynchronize(st));
                 if (op->d_units) cudaFree(op->d_units);
@@ -959,6 +979,11 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             RMB_CUDA(cudaStreamSynchronize(st));   // `units` is pageable host memory
             op->nunits = (int)units.size();
             op->units_nstates = nstates;
+        }
+        if (op->nnz_dirty) {
+            k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask);
+            op->nnz_dirty = false;
+            op->n_launches++;
         }
         if (op->k_complex)
             k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
@@ -976,7 +1001,7 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         if (op->unitsG_nstates != nstates) {
             std::vector<Unit2D> units;
             for (int i = 0; i < op->nitemsG; ++i)
-                for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0});
+                for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0, 1, 0});
             if ((int)units.size() > op->unitsG_cap) {
                 RMB_CUDA(cudaStreamSynchronize(st));
                 if (op->d_unitsG) cudaFree(op->d_unitsG);

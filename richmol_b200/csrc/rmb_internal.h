@@ -132,6 +132,8 @@ struct rmb_operator {
     int lin_W = 0, lin_T = 0, lin_dm_max = 0, lin_NS = 0, lin_npart = 0;
     size_t lin_smem = 0;
     bool lin_flat_dirty = true;      // entry lists must be rebuilt (field changed)
+    bool nnz_dirty = true;           // ProdS::nnz of the tiled-kernel descriptors must be refreshed (field changed)
+    int ngdesc = 0;
     int* d_prod_ket = nullptr;
     void* d_lin_blk = nullptr;       // LinBlk[nblocks]
     void* d_lin_flat = nullptr;      // LinEnt[nblocks][ML_FLAT]

@@ -42,7 +42,9 @@ struct Item2D {
 };
 
 struct XRange { int c_lo, nr; };   // ket rows [c_lo, c_lo + nr) needed by (item, product)
-struct Unit2D { int item, s0; };
+struct Unit2D { int item, s0, ntiles, pad; };   // `ntiles` consecutive state tiles (tiled kernel; 1 for the DMMA kernel)
+constexpr int MV2_TILES_MAX = 8;       // state tiles one CTA of the tiled kernel may walk
+constexpr int MV2_RED_BYTES = 4 * MV2_CONSUMERS * 8 + MV2_TILES_MAX * 4;   // <w,V_k> partials [2][nst][nrows] + tile flags
 
 // compacted MF entry (written by k_compact_tables): value and ket m index of one surviving diagonal
 struct __align__(32) MfEntry { double re, im; int col; int pad[3]; };
@@ -54,6 +56,13 @@ struct ProdS {
     long long ent_off;   // first compacted entry of the MF table
     int dk2, nnz, c_lo, nr, xrs, tab, pad1, pad2;
 };
+
+// After a field update: surviving diagonals per (item, product) descriptor, so that the descriptors a CTA copies to
+// shared memory are complete (no dependent gather from the diagonal masks at CTA start)
+__global__ void k_fill_nnz(int n, ProdS* __restrict__ gdesc, const unsigned* __restrict__ tab_mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gdesc[i].nnz = min(__popc(tab_mask[gdesc[i].tab]), MV2_NDMAX);
+}
 
 // ---- mbarrier / TMA (cp.async.bulk) helpers -----------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -217,7 +226,7 @@ struct Mv2Smem {
     double2* xbuf[MV2_STAGES];
     unsigned xbuf_b[MV2_STAGES]; // the same as byte offsets into rmb_dsmem
     unsigned mfe_b[MV2_STAGES];
-    unsigned kt_b, sp_b, snnz_b;
+    unsigned kt_b, sp_b, snnz_b, red_b;      // red: [2][nst][nrows] partial dots, then int flags[MV2_TILES_MAX]
     MfEntry* mfe[MV2_STAGES];
     double* kt;
     ProdS* sp;
@@ -239,102 +248,107 @@ struct Mv2Smem {
 template <int NC, bool KC>
 __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __restrict__ X,
                                              double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
-                                             int s0, const int* __restrict__ active, const Mv2Smem& sm,
+                                             int s0, int ntiles, const int* __restrict__ active, const Mv2Smem& sm,
                                              const double* __restrict__ scale, int scale_stride,
                                              double2* __restrict__ pdot, int npart, int item_index,
-                                             int sl, int rl, bool inb, bool vA, bool vB) {
+                                             int sl, int rl, bool inb) {
     constexpr int KW = KC ? 2 : 1;                       // doubles per K element
-    const int stA = s0 + 2 * sl, stB = stA + 1;
-    const bool work = vA || vB;
-    const int np = it.p_end - it.p_begin;
-    double2 accA[NC], accB[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
-
-    const int* snnz = reinterpret_cast<const int*>(rmb_dsmem + sm.snnz_b);
-    const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
-    mbar_wait(sm.setup, 0);
-    int ktbase = 0;
-    for (int ip = 0; ip < np; ++ip) {
-        const int stage = ip % MV2_STAGES;
-        mbar_wait(&sm.full[stage], (ip / MV2_STAGES) & 1);
-        const int dk2 = sp[ip].dk2, nnz = snnz[ip];
-        if (work) {
-            const int nr = sp[ip].nr, xrs = sp[ip].xrs, c_lo = sp[ip].c_lo;
-            const unsigned xa = sm.xbuf_b[stage] + (unsigned)((2 * sl) * nr * xrs) * 16u;
-            const unsigned xb = xa + (unsigned)(nr * xrs) * 16u;   // an inactive partner reads stale data: never stored
-            const unsigned mfe = sm.mfe_b[stage] + (unsigned)rl * (unsigned)sizeof(MfEntry);
-            const unsigned ktp = sm.kt_b + (unsigned)ktbase * 8u;
-            switch (nnz) {
-                case 0: break;
-                case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                default: mv2_inner<NC, 5, KC>(xa, xb, mfe, it.nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-            }
-        }
-        ktbase += dk2 * NC * KW;
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
-    }
-    // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
-    //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
-    double preA = 0.0, pimA = 0.0, preB = 0.0, pimB = 0.0;
+    const int np = it.p_end - it.p_begin, nrows = it.nrows, nst = it.nst, nc = it.nc;
     const long long row_off = it.bra_off + (long long)(it.r0 + rl) * (it.dk1 | 1) + it.c0;
-    auto finish = [&](double2 (&acc)[NC], int st, double& pre, double& pim) {
-        if (scale != nullptr) {
-            const double sc = scale[(long long)st * scale_stride];
+    const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
+    const int* tflag = reinterpret_cast<const int*>(rmb_dsmem + sm.red_b + 4 * MV2_CONSUMERS * 8);
+    mbar_wait(sm.setup, 0);
+    int g = 0;                                           // products consumed so far (stage / phase counter)
+    for (int t = 0; t < ntiles; ++t, s0 += nst) {
+        if (!tflag[t]) continue;                         // every state of the tile has converged
+        const int stA = s0 + 2 * sl, stB = stA + 1;
+        const bool vA = inb && stA < nstates && (active == nullptr || active[stA]);
+        const bool vB = inb && stB < nstates && (active == nullptr || active[stB]);
+        const bool work = vA || vB;
+        double2 accA[NC], accB[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) { acc[c].x *= sc; acc[c].y *= sc; }
-        }
-        if (Y != nullptr) {
-            double2* y = Y + (long long)st * ldy + row_off;
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-                if (c < it.nc) y[c] = acc[c];
-        }
-        if (pdot != nullptr) {
-            const double2* x = X + (long long)st * ldx + row_off;
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-                if (c < it.nc) {
-                    const double2 v = x[c];
-                    pre += acc[c].x * v.x + acc[c].y * v.y;
-                    pim += acc[c].x * v.y - acc[c].y * v.x;
+        for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
+        int ktbase = 0;
+        for (int ip = 0; ip < np; ++ip, ++g) {
+            const int stage = g % MV2_STAGES;
+            mbar_wait(&sm.full[stage], (g / MV2_STAGES) & 1);
+            const int dk2 = sp[ip].dk2, nnz = sp[ip].nnz;
+            if (work) {
+                const int nr = sp[ip].nr, xrs = sp[ip].xrs, c_lo = sp[ip].c_lo;
+                const unsigned xa = sm.xbuf_b[stage] + (unsigned)((2 * sl) * nr * xrs) * 16u;
+                const unsigned xb = xa + (unsigned)(nr * xrs) * 16u;   // an inactive partner reads stale data: never stored
+                const unsigned mfe = sm.mfe_b[stage] + (unsigned)rl * (unsigned)sizeof(MfEntry);
+                const unsigned ktp = sm.kt_b + (unsigned)ktbase * 8u;
+                switch (nnz) {
+                    case 0: break;
+                    case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+                    default: mv2_inner<NC, 5, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
                 }
-        }
-    };
-    if (vA) finish(accA, stA, preA, pimA);
-    if (vB) finish(accB, stB, preB, pimB);
-    if (pdot != nullptr) {
-        // consumer warps only (the producers have left): named barrier 1.  Every consumer has passed the last
-        // `full` wait, so all stages are consumed and the staging buffers are free
-        asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
-        double* red = reinterpret_cast<double*>(rmb_dsmem + sm.xbuf_b[0]);   // [2][nst][nrows]
-        const int half = it.nst * it.nrows;
-        if (inb) {
-            red[(2 * sl) * it.nrows + rl] = preA;
-            red[(2 * sl + 1) * it.nrows + rl] = preB;
-            red[half + (2 * sl) * it.nrows + rl] = pimA;
-            red[half + (2 * sl + 1) * it.nrows + rl] = pimB;
-        }
-        asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int s = warp; s < it.nst; s += MV2_CONSUMERS / 32) {
-            const int sg = s0 + s;
-            if (sg >= nstates || (active != nullptr && !active[sg])) continue;
-            double a = 0.0, b = 0.0;
-            for (int r = lane; r < it.nrows; r += 32) {
-                a += red[s * it.nrows + r];
-                b += red[half + s * it.nrows + r];
             }
+            ktbase += dk2 * NC * KW;
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
+        }
+        // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
+        //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
+        double preA = 0.0, pimA = 0.0, preB = 0.0, pimB = 0.0;
+        auto finish = [&](double2 (&acc)[NC], int st, double& pre, double& pim) {
+            if (scale != nullptr) {
+                const double sc = scale[(long long)st * scale_stride];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_down_sync(0xffffffffu, a, o);
-                b += __shfl_down_sync(0xffffffffu, b, o);
+                for (int c = 0; c < NC; ++c) { acc[c].x *= sc; acc[c].y *= sc; }
             }
-            if (lane == 0) pdot[(long long)sg * npart + item_index] = make_double2(a, b);
+            if (Y != nullptr) {
+                double2* y = Y + (long long)st * ldy + row_off;
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (c < nc) y[c] = acc[c];
+            }
+            if (pdot != nullptr) {
+                const double2* x = X + (long long)st * ldx + row_off;
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (c < nc) {
+                        const double2 v = x[c];
+                        pre += acc[c].x * v.x + acc[c].y * v.y;
+                        pim += acc[c].x * v.y - acc[c].y * v.x;
+                    }
+            }
+        };
+        if (vA) finish(accA, stA, preA, pimA);
+        if (vB) finish(accB, stB, preB, pimB);
+        if (pdot != nullptr) {
+            // consumer warps only (named barrier 1; the producers are already staging the next tile).  The first
+            // barrier keeps a fast warp from overwriting the partials of the previous tile while they are read
+            asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
+            double* red = reinterpret_cast<double*>(rmb_dsmem + sm.red_b);   // [2][nst][nrows]
+            const int half = nst * nrows;
+            if (inb) {
+                red[(2 * sl) * nrows + rl] = preA;
+                red[(2 * sl + 1) * nrows + rl] = preB;
+                red[half + (2 * sl) * nrows + rl] = pimA;
+                red[half + (2 * sl + 1) * nrows + rl] = pimB;
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(MV2_CONSUMERS) : "memory");
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int s = warp; s < nst; s += MV2_CONSUMERS / 32) {
+                const int sg = s0 + s;
+                if (sg >= nstates || (active != nullptr && !active[sg])) continue;
+                double a = 0.0, b = 0.0;
+                for (int r = lane; r < nrows; r += 32) {
+                    a += red[s * nrows + r];
+                    b += red[half + s * nrows + r];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_down_sync(0xffffffffu, a, o);
+                    b += __shfl_down_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) pdot[(long long)sg * npart + item_index] = make_double2(a, b);
+            }
         }
     }
 }
@@ -343,12 +357,11 @@ __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __
 __device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __restrict__ gdesc,
                                              const MfEntry* __restrict__ cent, const unsigned* __restrict__ tab_mask,
                                              const double* __restrict__ ktpool, const double2* __restrict__ X,
-                                             long long ldx, int nstates, int s0, const int* __restrict__ active,
-                                             const Mv2Smem& sm) {
+                                             long long ldx, int nstates, int s0, int ntiles,
+                                             const int* __restrict__ active, const Mv2Smem& sm) {
     const int np = it.p_end - it.p_begin;
     const int pw = (threadIdx.x - MV2_CONSUMERS) >> 5;    // producer warp: copies the states s % MV2_PRODUCERS == pw
     const int lane = threadIdx.x & 31;
-    int* wnnz = reinterpret_cast<int*>(rmb_dsmem + sm.snnz_b);
     const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
     if (pw == 0) {
         // the K^T image of all products and the static descriptors were laid out on the host exactly as
@@ -359,44 +372,39 @@ __device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __re
             if (kbytes) tma_load_1d(sm.kt, ktpool + it.kt_off, kbytes, sm.setup);
             if (dbytes) tma_load_1d(sm.sp, gdesc + it.desc_off, dbytes, sm.setup);
         }
-        // diagonals that survived the field contraction (field-dependent: read from the masks).  nnz goes to
-        // its own shared array (the descriptors are still in flight); the setup barrier completes when the
-        // bulk copies have landed and every lane of this warp has published its values
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ip = lane + 32 * j;
-            if (ip < np) wnnz[ip] = min(__popc(tab_mask[gdesc[it.desc_off + ip].tab]), MV2_NDMAX);
-        }
-        mbar_arrive(sm.setup);                           // release: snnz visible to whoever waits
     }
-    // state offset handled by this lane
-    long long sb = -1;
-    const int sidx = lane * MV2_PRODUCERS + pw;
-    if (sidx < it.nst) {
-        const int s = s0 + sidx;
-        if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
-    }
-    const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
+    const int* tflag = reinterpret_cast<const int*>(rmb_dsmem + sm.red_b + 4 * MV2_CONSUMERS * 8);
+    const int sidx = lane * MV2_PRODUCERS + pw;           // state of the tile handled by this lane
     mbar_wait(sm.setup, 0);
-    for (int ip = 0; ip < np; ++ip) {
-        const int stage = ip % MV2_STAGES;
-        if (ip >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((ip / MV2_STAGES) - 1) & 1);
-        const ProdS d = sp[ip];
-        const int nnz = pw == 0 ? wnnz[ip] : 0;          // warp 0 also brings the MF diagonals
-        const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
-        const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
-        if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
-        __syncwarp();
-        if (xbytes > 0 && sb >= 0)
-            tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
-                        &sm.full[stage]);
-        if (it.nrows == it.dm1) {
-            // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
-            if (lane == 0 && nnz > 0)
-                tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
-        } else if (lane < nnz) {
-            tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
-                        mbytes, &sm.full[stage]);
+    int g = 0;                                            // products staged so far (stage / phase counter)
+    for (int t = 0; t < ntiles; ++t, s0 += it.nst) {
+        if (!tflag[t]) continue;
+        long long sb = -1;
+        if (sidx < it.nst) {
+            const int s = s0 + sidx;
+            if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
+        }
+        const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
+        for (int ip = 0; ip < np; ++ip, ++g) {
+            const int stage = g % MV2_STAGES;
+            if (g >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((g / MV2_STAGES) - 1) & 1);
+            const ProdS d = sp[ip];
+            const int nnz = pw == 0 ? d.nnz : 0;             // warp 0 also brings the MF diagonals (k_fill_nnz)
+            const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
+            const unsigned mbytes = (unsigned)it.nrows * (unsigned)sizeof(MfEntry);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
+            __syncwarp();
+            if (xbytes > 0 && sb >= 0)
+                tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
+                            &sm.full[stage]);
+            if (it.nrows == it.dm1) {
+                // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
+                if (lane == 0 && nnz > 0)
+                    tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
+            } else if (lane < nnz) {
+                tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
+                            mbytes, &sm.full[stage]);
+            }
         }
     }
 }
@@ -430,17 +438,26 @@ k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ item
     sm.sp = reinterpret_cast<ProdS*>(p); sm.sp_b = (unsigned)(p - smem_raw); p += (size_t)np * sizeof(ProdS);
     sm.full = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
     sm.empty = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
-    sm.setup = reinterpret_cast<unsigned long long*>(p);     // followed by int snnz[np]
+    sm.setup = reinterpret_cast<unsigned long long*>(p);
     sm.snnz_b = (unsigned)(p + 8 - smem_raw);
+    p += 8 + (((size_t)np * 4 + 15) & ~(size_t)15);
+    sm.red_b = (unsigned)(p - smem_raw);
 
     const bool producer = threadIdx.x >= MV2_CONSUMERS;
     const int sl = threadIdx.x / it.nrows;               // state pair of this thread
     const int rl = threadIdx.x - sl * it.nrows;
-    const int stA = u.s0 + 2 * sl, stB = stA + 1;
     const bool inb = !producer && 2 * sl < it.nst;
-    const bool vA = inb && stA < nstates && (active == nullptr || active[stA]);
-    const bool vB = inb && stB < nstates && (active == nullptr || active[stB]);
-    if (__syncthreads_or(vA || vB) == 0) return;         // every state of the tile has converged
+    // which of the unit's state tiles still have work (converged states are skipped at tile granularity)
+    int* tflag = reinterpret_cast<int*>(smem_raw + sm.red_b + 4 * MV2_CONSUMERS * 8);
+    if (threadIdx.x < MV2_TILES_MAX) tflag[threadIdx.x] = 0;
+    __syncthreads();
+    bool mine = false;
+    {
+        const int t = threadIdx.x / it.nst;              // nst <= 32, ntiles <= 8: one thread per (tile, state)
+        const int s = u.s0 + threadIdx.x;
+        if (t < u.ntiles && s < nstates && (active == nullptr || active[s])) { tflag[t] = 1; mine = true; }
+    }
+    if (__syncthreads_or(mine) == 0) return;             // every state of the unit has converged
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -448,21 +465,21 @@ k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ item
             mbar_init(&sm.full[i], MV2_PRODUCERS);           // lane 0 of every producer warp (arrive.expect_tx) + tx bytes
             mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
         }
-        mbar_init(sm.setup, 1 + 32);                         // expect_tx arrival + every lane of producer warp 0
+        mbar_init(sm.setup, 1);                              // the expect_tx arrival of the K^T / descriptor copies
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
     if (producer) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(MV2_REGS_PRODUCER));
-        mv2_producer(it, gdesc, cent, tab_mask, ktpool, X, ldx, nstates, u.s0, active, sm);
+        mv2_producer(it, gdesc, cent, tab_mask, ktpool, X, ldx, nstates, u.s0, u.ntiles, active, sm);
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(MV2_REGS_CONSUMER));
 #define RMB_CASE(N)                                                                                        \
     case N:                                                                                                \
-        mv2_consumer<N, KC>(it, X, Y, ldx, ldy, nstates, u.s0, active, sm, scale, scale_stride, pdot,      \
-                            npart, u.item, sl, rl, inb, vA, vB);                                           \
+        mv2_consumer<N, KC>(it, X, Y, ldx, ldy, nstates, u.s0, u.ntiles, active, sm, scale, scale_stride,  \
+                            pdot, npart, u.item, sl, rl, inb);                                             \
         break;
     switch (it.nc == 1 ? 1 : (it.nc + 1) & ~1) {
         RMB_CASE(1) RMB_CASE(2) RMB_CASE(4) RMB_CASE(6) RMB_CASE(8)
