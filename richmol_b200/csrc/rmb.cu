@@ -331,10 +331,12 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             }
         h_span[p] = hi >= lo ? hi - lo : 0;
     }
-    auto item_smem = [](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod) {
-        return (size_t)MV2_STAGES * xbuf_elems * 16 + (size_t)MV2_STAGES * MV2_NDMAX * nrows * sizeof(MfEntry) +
-               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (2 * MV2_STAGES + 1) * 8 + (size_t)nprod * 4 + 16 +
-               MV2_RED_BYTES + 128;
+    auto item_smem_st = [](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod, int stages) {
+        return (size_t)stages * xbuf_elems * 16 + (size_t)stages * MV2_NDMAX * nrows * sizeof(MfEntry) +
+               kt_doubles * 8 + (size_t)nprod * sizeof(ProdS) + (size_t)(2 * stages) * 8 + 16 + MV2_RED_BYTES + 128;
+    };
+    auto item_smem = [&](size_t xbuf_elems, int nrows, size_t kt_doubles, int nprod) {
+        return item_smem_st(xbuf_elems, nrows, kt_doubles, nprod, MV2_STAGES);
     };
     const char* force = getenv("RMB_MATVEC");
     auto itemG_smem = [](size_t xbuf_elems, int nrows, int ldk) {
@@ -556,8 +558,17 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             it.kt_off = found->second;
                         }
                         it.xbuf_elems = xbe;
+                        // every CTA reserves the maximum over items anyway: small items use it for a deeper pipeline
+                        // (their products compute faster than a bulk copy takes to land)
+                        it.nstages = MV2_STAGES;
+                        while (it.nstages < MV2_STAGES_MAX && it.nstages < it.p_end - it.p_begin &&
+                               item_smem_st((size_t)xbe, it.nrows, (size_t)it.kt_total, it.p_end - it.p_begin,
+                                            it.nstages + 1) <= smem_budget)
+                            ++it.nstages;
+                        if (const char* e = getenv("RMB_MV2_STAGES")) it.nstages = std::min(it.nstages, std::max(MV2_STAGES, atoi(e)));
                         op->matvec2_smem = std::max(op->matvec2_smem,
-                                                    item_smem((size_t)xbe, it.nrows, (size_t)it.kt_total, it.p_end - it.p_begin));
+                                                    item_smem_st((size_t)xbe, it.nrows, (size_t)it.kt_total,
+                                                                 it.p_end - it.p_begin, it.nstages));
                         items2.push_back(it);
                     }
                 continue;
@@ -618,8 +629,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         fprintf(stderr, "[rmb] tiled items %d (smem %zu B), DMMA items %d (smem %zu B), scalar items %zu\n",
                 op->nitems2, op->matvec2_smem, op->nitemsG, op->matvecG_smem, op->h_items.size());
         for (auto& it : items2)
-            fprintf(stderr, "[rmb]   item dm1 %d dk1 %d rows %d nc %d nst %d products %d xbuf %d B kt %d B\n", it.dm1,
-                    it.dk1, it.nrows, it.nc, it.nst, it.p_end - it.p_begin, it.xbuf_elems * 16, it.kt_total * 8);
+            fprintf(stderr, "[rmb]   item dm1 %d dk1 %d rows %d nc %d nst %d products %d stages %d xbuf %d B kt %d B\n", it.dm1,
+                    it.dk1, it.nrows, it.nc, it.nst, it.p_end - it.p_begin, it.nstages, it.xbuf_elems * 16, it.kt_total * 8);
     }
 
     opbytes += 20.0 * (double)op->nent;   // MF values + column indices

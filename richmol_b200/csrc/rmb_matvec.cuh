@@ -25,7 +25,8 @@ constexpr int MV2_REGS_CONSUMER = 208;
 constexpr int MV2_NCMAX = 12;     // columns (k1) per thread
 constexpr int MV2_NDMAX = 5;      // max ELL width handled by the tiled kernel (rank <= 2)
 constexpr int MV2_SMAX = 32;      // max states per CTA
-constexpr int MV2_STAGES = 2;     // products in flight
+constexpr int MV2_STAGES = 2;     // products in flight: minimum (sizes the state tile) ...
+constexpr int MV2_STAGES_MAX = 6; // ... and maximum per item (Item2D::nstages: as many as fit the shared-memory budget)
 
 struct Item2D {
     long long bra_off;
@@ -38,6 +39,7 @@ struct Item2D {
     int kt_total;        // doubles of K^T staged in shared memory for this item (even)
     int xbuf_elems;      // elements of one staging buffer: max over products of nst * nr * (dk2 | 1)
     int desc_off;        // first static descriptor (ProdS) of the item in the global descriptor table
+    int nstages;         // pipeline stages of this item (MV2_STAGES .. MV2_STAGES_MAX)
     long long kt_off;    // offset (doubles) of the item's K^T image in the global K^T pool
 };
 
@@ -223,16 +225,15 @@ __device__ __forceinline__ void mv2_inner(unsigned xa_byte, unsigned xb_byte, un
 }
 
 struct Mv2Smem {
-    double2* xbuf[MV2_STAGES];
-    unsigned xbuf_b[MV2_STAGES]; // the same as byte offsets into rmb_dsmem
-    unsigned mfe_b[MV2_STAGES];
-    unsigned kt_b, sp_b, snnz_b, red_b;      // red: [2][nst][nrows] partial dots, then int flags[MV2_TILES_MAX]
-    MfEntry* mfe[MV2_STAGES];
+    unsigned xbuf_b, xstride;    // ket staging buffers: byte offset of stage 0 in rmb_dsmem, bytes per stage
+    unsigned mfe_b, mstride;     // MF diagonal staging buffers
+    unsigned kt_b, sp_b, red_b;  // K^T image, descriptors; red: [2][nst][nrows] partial dots, then int flags[MV2_TILES_MAX]
+    int nstages;
     double* kt;
     ProdS* sp;
-    unsigned long long* full;    // [MV2_STAGES] data of a product has landed (TMA transaction bytes)
-    unsigned long long* empty;   // [MV2_STAGES] every consumer warp is done with the stage
-    unsigned long long* setup;   // K^T image + descriptors have landed, nnz filled in
+    unsigned long long* full;    // [nstages] data of a product has landed (TMA transaction bytes)
+    unsigned long long* empty;   // [nstages] every consumer warp is done with the stage
+    unsigned long long* setup;   // K^T image + descriptors have landed
 };
 
 // K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, state tile).
@@ -258,7 +259,7 @@ __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __
     const ProdS* sp = reinterpret_cast<const ProdS*>(rmb_dsmem + sm.sp_b);
     const int* tflag = reinterpret_cast<const int*>(rmb_dsmem + sm.red_b + 4 * MV2_CONSUMERS * 8);
     mbar_wait(sm.setup, 0);
-    int g = 0;                                           // products consumed so far (stage / phase counter)
+    int stage = 0, phase = 0;                            // pipeline position of the next product
     for (int t = 0; t < ntiles; ++t, s0 += nst) {
         if (!tflag[t]) continue;                         // every state of the tile has converged
         const int stA = s0 + 2 * sl, stB = stA + 1;
@@ -269,15 +270,14 @@ __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __
 #pragma unroll
         for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
         int ktbase = 0;
-        for (int ip = 0; ip < np; ++ip, ++g) {
-            const int stage = g % MV2_STAGES;
-            mbar_wait(&sm.full[stage], (g / MV2_STAGES) & 1);
+        for (int ip = 0; ip < np; ++ip) {
+            mbar_wait(&sm.full[stage], (unsigned)phase);
             const int dk2 = sp[ip].dk2, nnz = sp[ip].nnz;
             if (work) {
                 const int nr = sp[ip].nr, xrs = sp[ip].xrs, c_lo = sp[ip].c_lo;
-                const unsigned xa = sm.xbuf_b[stage] + (unsigned)((2 * sl) * nr * xrs) * 16u;
+                const unsigned xa = sm.xbuf_b + (unsigned)stage * sm.xstride + (unsigned)((2 * sl) * nr * xrs) * 16u;
                 const unsigned xb = xa + (unsigned)(nr * xrs) * 16u;   // an inactive partner reads stale data: never stored
-                const unsigned mfe = sm.mfe_b[stage] + (unsigned)rl * (unsigned)sizeof(MfEntry);
+                const unsigned mfe = sm.mfe_b + (unsigned)stage * sm.mstride + (unsigned)rl * (unsigned)sizeof(MfEntry);
                 const unsigned ktp = sm.kt_b + (unsigned)ktbase * 8u;
                 switch (nnz) {
                     case 0: break;
@@ -291,6 +291,7 @@ __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __
             ktbase += dk2 * NC * KW;
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
+            if (++stage == sm.nstages) { stage = 0; phase ^= 1; }
         }
         // ---- epilogue: optional per-state scale (w = rinv_k * H slab_k), store, fused partial dot
         //      sum conj(w) * x over the rows of this tile (alpha of the Lanczos recurrence, tdse.py:468)
@@ -376,7 +377,7 @@ __device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __re
     const int* tflag = reinterpret_cast<const int*>(rmb_dsmem + sm.red_b + 4 * MV2_CONSUMERS * 8);
     const int sidx = lane * MV2_PRODUCERS + pw;           // state of the tile handled by this lane
     mbar_wait(sm.setup, 0);
-    int g = 0;                                            // products staged so far (stage / phase counter)
+    int stage = 0, phase = 1;                             // next stage to fill; parity of its `empty` barrier
     for (int t = 0; t < ntiles; ++t, s0 += it.nst) {
         if (!tflag[t]) continue;
         long long sb = -1;
@@ -385,9 +386,9 @@ __device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __re
             if (s < nstates && (active == nullptr || active[s])) sb = (long long)s * ldx;
         }
         const int nact = __popc(__ballot_sync(0xffffffffu, sb >= 0));
-        for (int ip = 0; ip < np; ++ip, ++g) {
-            const int stage = g % MV2_STAGES;
-            if (g >= MV2_STAGES) mbar_wait(&sm.empty[stage], ((g / MV2_STAGES) - 1) & 1);
+        for (int ip = 0; ip < np; ++ip) {
+            // (a fresh barrier passes a wait on parity 1: the first round over the stages does not block)
+            mbar_wait(&sm.empty[stage], (unsigned)phase);
             const ProdS d = sp[ip];
             const int nnz = pw == 0 ? d.nnz : 0;             // warp 0 also brings the MF diagonals (k_fill_nnz)
             const unsigned xbytes = (unsigned)(d.nr * d.xrs) * 16u;
@@ -395,16 +396,18 @@ __device__ __forceinline__ void mv2_producer(const Item2D& it, const ProdS* __re
             if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (unsigned)nact * xbytes + (unsigned)nnz * mbytes);
             __syncwarp();
             if (xbytes > 0 && sb >= 0)
-                tma_load_1d(sm.xbuf[stage] + (long long)sidx * d.nr * d.xrs, X + sb + d.ket_off, xbytes,
-                            &sm.full[stage]);
+                tma_load_1d(rmb_dsmem + sm.xbuf_b + (unsigned)stage * sm.xstride + (unsigned)(sidx * d.nr * d.xrs) * 16u,
+                            X + sb + d.ket_off, xbytes, &sm.full[stage]);
             if (it.nrows == it.dm1) {
                 // the tile covers every row of the bra block: the surviving diagonals are one contiguous run
                 if (lane == 0 && nnz > 0)
-                    tma_load_1d(sm.mfe[stage], cent + d.ent_off, (unsigned)nnz * mbytes, &sm.full[stage]);
+                    tma_load_1d(rmb_dsmem + sm.mfe_b + (unsigned)stage * sm.mstride, cent + d.ent_off, (unsigned)nnz * mbytes,
+                                &sm.full[stage]);
             } else if (lane < nnz) {
-                tma_load_1d(sm.mfe[stage] + lane * it.nrows, cent + d.ent_off + (long long)lane * it.dm1 + it.r0,
-                            mbytes, &sm.full[stage]);
+                tma_load_1d(rmb_dsmem + sm.mfe_b + (unsigned)stage * sm.mstride + (unsigned)(lane * it.nrows) * (unsigned)sizeof(MfEntry),
+                            cent + d.ent_off + (long long)lane * it.dm1 + it.r0, mbytes, &sm.full[stage]);
             }
+            if (++stage == sm.nstages) { stage = 0; phase ^= 1; }
         }
     }
 }
@@ -424,23 +427,19 @@ k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ item
     // shared memory is carved with the sizes of this item (the launch reserves the maximum over items)
     Mv2Smem sm;
     unsigned char* p = smem_raw;
-    for (int i = 0; i < MV2_STAGES; ++i) {
-        sm.xbuf[i] = reinterpret_cast<double2*>(p);
-        sm.xbuf_b[i] = (unsigned)(p - smem_raw);
-        p += (size_t)it.xbuf_elems * 16;
-    }
-    for (int i = 0; i < MV2_STAGES; ++i) {
-        sm.mfe[i] = reinterpret_cast<MfEntry*>(p);
-        sm.mfe_b[i] = (unsigned)(p - smem_raw);
-        p += (size_t)MV2_NDMAX * it.nrows * sizeof(MfEntry);
-    }
+    sm.nstages = it.nstages;
+    sm.xbuf_b = 0;
+    sm.xstride = (unsigned)it.xbuf_elems * 16u;
+    p += (size_t)it.nstages * sm.xstride;
+    sm.mfe_b = (unsigned)(p - smem_raw);
+    sm.mstride = (unsigned)(MV2_NDMAX * it.nrows) * (unsigned)sizeof(MfEntry);
+    p += (size_t)it.nstages * sm.mstride;
     sm.kt = reinterpret_cast<double*>(p); sm.kt_b = (unsigned)(p - smem_raw); p += (size_t)it.kt_total * 8;
     sm.sp = reinterpret_cast<ProdS*>(p); sm.sp_b = (unsigned)(p - smem_raw); p += (size_t)np * sizeof(ProdS);
-    sm.full = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
-    sm.empty = reinterpret_cast<unsigned long long*>(p); p += MV2_STAGES * 8;
+    sm.full = reinterpret_cast<unsigned long long*>(p); p += it.nstages * 8;
+    sm.empty = reinterpret_cast<unsigned long long*>(p); p += it.nstages * 8;
     sm.setup = reinterpret_cast<unsigned long long*>(p);
-    sm.snnz_b = (unsigned)(p + 8 - smem_raw);
-    p += 8 + (((size_t)np * 4 + 15) & ~(size_t)15);
+    p += 16;
     sm.red_b = (unsigned)(p - smem_raw);
 
     const bool producer = threadIdx.x >= MV2_CONSUMERS;
@@ -460,8 +459,7 @@ k_matvec_tiled(const Unit2D* __restrict__ units, const Item2D* __restrict__ item
     if (__syncthreads_or(mine) == 0) return;             // every state of the unit has converged
 
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < MV2_STAGES; ++i) {
+        for (int i = 0; i < it.nstages; ++i) {
             mbar_init(&sm.full[i], MV2_PRODUCERS);           // lane 0 of every producer warp (arrive.expect_tx) + tx bytes
             mbar_init(&sm.empty[i], MV2_CONSUMERS / 32);     // one arrival per consumer warp
         }
