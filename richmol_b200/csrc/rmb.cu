@@ -72,10 +72,10 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_lin_val_off);
     cudaFree(op->d_items2);
     cudaFree(op->d_itemsG);
-    cudaFree(op->d_unitsG);
+    for (auto& kv : op->unitsG_cache) cudaFree(kv.second.first);
     cudaFree(op->d_gdesc);
     cudaFree(op->d_ktpool);
-    cudaFree(op->d_units);
+    for (auto& kv : op->units_cache) cudaFree(kv.second.first);
     cudaFree(op->d_ent_col);
     cudaFree(op->d_ent_val);
     cudaFree(op->d_ent_cent);
@@ -966,29 +966,36 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
     if (op->nitems2 > 0) {
         // work units (item, first state) for this batch size; rebuilt only when the size changes
         if (op->units_nstates != nstates) {
-            // a CTA walks `tiles` consecutive state tiles of one item (K^T image, descriptors and pipeline set up
-            // once); fewer, longer CTAs as long as the grid still fills the 2 x 148 CTA slots several times over
-            std::vector<Unit2D> units;
-            long long ntile_total = 0;
-            for (int i = 0; i < op->nitems2; ++i) ntile_total += (nstates + op->h_item2_states[i] - 1) / op->h_item2_states[i];
-            int tiles = (int)std::max<long long>(1, std::min<long long>(MV2_TILES_MAX, ntile_total / (6 * 2 * 148)));
-            if (const char* e = getenv("RMB_MV2_TILES")) tiles = std::max(1, std::min(MV2_TILES_MAX, atoi(e)));
-            for (int i = 0; i < op->nitems2; ++i) {
-                const long long nst = op->h_item2_states[i];
-                const int tl = (int)std::min<long long>(tiles, std::max<long long>(1, 256 / nst));   // one flag thread per state
-                for (long long s0 = 0; s0 < nstates; s0 += nst * tl)
-                    units.push_back({i, (int)s0, (int)std::min<long long>(tl, (nstates - s0 + nst - 1) / nst), 0});
+            auto hit = op->units_cache.find(nstates);
+            if (hit == op->units_cache.end()) {
+                // a CTA walks `tiles` consecutive state tiles of one item (K^T image, descriptors and pipeline set up
+                // once); fewer, longer CTAs as long as the grid still fills the 2 x 148 CTA slots several times over
+                std::vector<Unit2D> units;
+                long long ntile_total = 0;
+                for (int i = 0; i < op->nitems2; ++i) ntile_total += (nstates + op->h_item2_states[i] - 1) / op->h_item2_states[i];
+                int tiles = (int)std::max<long long>(1, std::min<long long>(MV2_TILES_MAX, ntile_total / (6 * 2 * 148)));
+                if (const char* e = getenv("RMB_MV2_TILES")) tiles = std::max(1, std::min(MV2_TILES_MAX, atoi(e)));
+                for (int i = 0; i < op->nitems2; ++i) {
+                    const long long nst = op->h_item2_states[i];
+                    const int tl = (int)std::min<long long>(tiles, std::max<long long>(1, 256 / nst));   // one flag thread per state
+                    for (long long s0 = 0; s0 < nstates; s0 += nst * tl)
+                        units.push_back({i, (int)s0, (int)std::min<long long>(tl, (nstates - s0 + nst - 1) / nst), 0});
+                }
+                // the lists of the batch sizes in use are kept (the chunks of the host-buffer pipeline and the
+                // sub-batches of a large ensemble alternate between two or three sizes)
+                if (op->units_cache.size() >= 16) {
+                    RMB_CUDA(cudaStreamSynchronize(st));
+                    for (auto& kv : op->units_cache) cudaFree(kv.second.first);
+                    op->units_cache.clear();
+                }
+                void* d = nullptr;
+                RMB_CUDA(cudaMalloc(&d, sizeof(Unit2D) * std::max<size_t>(1, units.size())));
+                RMB_CUDA(cudaMemcpyAsync(d, units.data(), sizeof(Unit2D) * units.size(), cudaMemcpyHostToDevice, st));
+                RMB_CUDA(cudaStreamSynchronize(st));   // `units` is pageable host memory
+                hit = op->units_cache.emplace(nstates, std::make_pair(d, (int)units.size())).first;
             }
-            if ((int)units.size() > op->units_cap) {
-                RMB_CUDA(cudaStreamSynchronize(st));
-                if (op->d_units) cudaFree(op->d_units);
-                op->units_cap = (int)units.size();
-                RMB_CUDA(cudaMalloc(&op->d_units, sizeof(Unit2D) * op->units_cap));
-            }
-            RMB_CUDA(cudaMemcpyAsync(op->d_units, units.data(), sizeof(Unit2D) * units.size(),
-                                     cudaMemcpyHostToDevice, st));
-            RMB_CUDA(cudaStreamSynchronize(st));   // `units` is pageable host memory
-            op->nunits = (int)units.size();
+            op->d_units = hit->second.first;
+            op->nunits = hit->second.second;
             op->units_nstates = nstates;
         }
         if (op->nnz_dirty) {
@@ -1010,19 +1017,24 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
     }
     if (op->nitemsG > 0) {
         if (op->unitsG_nstates != nstates) {
-            std::vector<Unit2D> units;
-            for (int i = 0; i < op->nitemsG; ++i)
-                for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0, 1, 0});
-            if ((int)units.size() > op->unitsG_cap) {
+            auto hit = op->unitsG_cache.find(nstates);
+            if (hit == op->unitsG_cache.end()) {
+                std::vector<Unit2D> units;
+                for (int i = 0; i < op->nitemsG; ++i)
+                    for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0, 1, 0});
+                if (op->unitsG_cache.size() >= 16) {
+                    RMB_CUDA(cudaStreamSynchronize(st));
+                    for (auto& kv : op->unitsG_cache) cudaFree(kv.second.first);
+                    op->unitsG_cache.clear();
+                }
+                void* d = nullptr;
+                RMB_CUDA(cudaMalloc(&d, sizeof(Unit2D) * std::max<size_t>(1, units.size())));
+                RMB_CUDA(cudaMemcpyAsync(d, units.data(), sizeof(Unit2D) * units.size(), cudaMemcpyHostToDevice, st));
                 RMB_CUDA(cudaStreamSynchronize(st));
-                if (op->d_unitsG) cudaFree(op->d_unitsG);
-                op->unitsG_cap = (int)units.size();
-                RMB_CUDA(cudaMalloc(&op->d_unitsG, sizeof(Unit2D) * op->unitsG_cap));
+                hit = op->unitsG_cache.emplace(nstates, std::make_pair(d, (int)units.size())).first;
             }
-            RMB_CUDA(cudaMemcpyAsync(op->d_unitsG, units.data(), sizeof(Unit2D) * units.size(),
-                                     cudaMemcpyHostToDevice, st));
-            RMB_CUDA(cudaStreamSynchronize(st));
-            op->nunitsG = (int)units.size();
+            op->d_unitsG = hit->second.first;
+            op->nunitsG = hit->second.second;
             op->unitsG_nstates = nstates;
         }
         k_matvec_gemm<<<op->nunitsG, MG_THREADS, op->matvecG_smem, st>>>(

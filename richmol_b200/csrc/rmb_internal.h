@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/richmol_b200.h"
@@ -97,16 +98,16 @@ struct rmb_operator {
     void* d_items2 = nullptr;        // Item2D[]
     void* d_gdesc = nullptr;         // ProdS[]: static per-(item, product) descriptors
     double* d_ktpool = nullptr;      // K^T images in shared-memory layout
-    void* d_units = nullptr;         // Unit2D[] for `units_nstates` states
+    void* d_units = nullptr;         // Unit2D[] for `units_nstates` states (owned by units_cache)
+    std::map<long long, std::pair<void*, int>> units_cache, unitsG_cache;   // batch size -> device unit list
     long long units_nstates = -1;
     int nunits = 0;
-    int units_cap = 0;
     std::vector<int> h_item2_states; // states per CTA of each tiled item
     // DMMA matvec for wide K blocks (rmb_matvec_gemm.cuh)
     int nitemsG = 0;
     void* d_itemsG = nullptr;        // ItemG[]
     void* d_unitsG = nullptr;
-    int nunitsG = 0, unitsG_cap = 0;
+    int nunitsG = 0;
     long long unitsG_nstates = -1;
     std::vector<int> h_itemG_states;
     size_t matvecG_smem = 0;

@@ -432,7 +432,24 @@ k_recur_conv(const cplx* __restrict__ w, cplx* const* __restrict__ slabs, long l
             nr += cabs2(r);
         }
     }
-    for (int j = 0; j + 2 <= k; ++j) {
+    // older Krylov vectors, two per trip: all 2 x VEC_PER_THREAD loads of a trip are issued before the first use
+    // (the kernel is latency-bound otherwise: 52 % of the HBM peak with one vector per trip)
+    int j = 0;
+    for (; j + 3 <= k; j += 2) {
+        const cplx* v0 = slabs[j] + s * ldv;
+        const cplx* v1 = slabs[j + 1] + s * ldv;
+        const cplx c0 = sdc[j], c1 = sdc[j + 1];
+        cplx t0[VEC_PER_THREAD], t1[VEC_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < VEC_PER_THREAD; ++i) {
+            const long long x = base + threadIdx.x + i * VEC_THREADS;
+            t0[i] = t1[i] = make_double2(0.0, 0.0);
+            if (x < n) { t0[i] = v0[x]; t1[i] = v1[x]; }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC_PER_THREAD; ++i) { cfma(d[i], c0, t0[i]); cfma(d[i], c1, t1[i]); }
+    }
+    for (; j + 2 <= k; ++j) {
         const cplx* vj = slabs[j] + s * ldv;
         const cplx c = sdc[j];
 #pragma unroll
@@ -552,7 +569,22 @@ k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cpl
         const long long x = base + threadIdx.x + i * VEC_THREADS;
         xp[i] = x < n ? pmap[x] : 0;
     }
-    for (int j = 0; j <= k; ++j) {
+    int j = 0;
+    for (; j + 1 <= k; j += 2) {                  // two Krylov vectors per trip (all loads issued before the first use)
+        const cplx* v0 = slabs[j] + s * ldv;
+        const cplx* v1 = slabs[j + 1] + s * ldv;
+        const cplx c0 = sc[j], c1 = sc[j + 1];
+        cplx t0[VEC_PER_THREAD], t1[VEC_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < VEC_PER_THREAD; ++i) {
+            const long long x = base + threadIdx.x + i * VEC_THREADS;
+            t0[i] = t1[i] = make_double2(0.0, 0.0);
+            if (x < n) { t0[i] = v0[xp[i]]; t1[i] = v1[xp[i]]; }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC_PER_THREAD; ++i) { cfma(u[i], c0, t0[i]); cfma(u[i], c1, t1[i]); }
+    }
+    for (; j <= k; ++j) {
         const cplx* vj = slabs[j] + s * ldv;
         const cplx c = sc[j];
 #pragma unroll
