@@ -336,7 +336,7 @@ def gpu_run(args):
     # reads come from L2 and the state vectors are the only compulsory DRAM traffic)
     compute_bound = ai > 1.25 * ridge
     head = fp64 if compute_bound else hbm
-    kernel = ("k_matvec_tiled (H.Psi: TMA-staged ket rows, fused MF(x)K block products, fused <w,V_k>)"
+    kernel = ("k_matvec_tiled (H.Psi: warpgroup-specialised, TMA-staged ket rows, fused MF(x)K block products, fused <w,V_k>)"
               if args.workload == "h2o" else
               "k_matvec_lin (H.Psi of a linear rotor: sliding window of ket blocks in shared memory, fused <w,V_k>)")
     roofline = {
