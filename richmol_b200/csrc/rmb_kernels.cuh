@@ -5,6 +5,10 @@
 
 namespace rmb {
 
+#ifndef RMB_VEC_MINB
+#define RMB_VEC_MINB 6       // CTAs per SM requested for k_recur_conv / k_combine (40 registers, a few spills): measured faster and
+                             // steadier than 4 CTAs at 64 registers (OCS, 120 steps: 5.5 vs 6.5-7.7 ms per step)
+#endif
 constexpr int VEC_THREADS = 256;
 constexpr int VEC_PER_THREAD = 4;
 constexpr int VEC_CHUNK = VEC_THREADS * VEC_PER_THREAD;   // complex elements per CTA of the vector kernels
@@ -392,7 +396,7 @@ k_small_a(const cplx* __restrict__ pdot, int npart, cplx* __restrict__ alpha, co
 
 // W_k = w - alpha_k V_k - beta_k V_{k-1}  (tdse.py:446,469-470) written to slab k+1, partial |W_k|^2,
 // and partial | sum_i dc_i V_i |^2  (u_k - u_{k-1}, tdse.py:475-476) in the same pass
-__global__ void __launch_bounds__(VEC_THREADS)
+__global__ void __launch_bounds__(VEC_THREADS, RMB_VEC_MINB)
 k_recur_conv(const cplx* __restrict__ w, cplx* const* __restrict__ slabs, long long ldv, long long n,
              const cplx* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ rinv,
              const cplx* __restrict__ dceff, int tstride, int bstride, int k, double* __restrict__ pnrm,
@@ -550,7 +554,7 @@ k_small_b(const double* __restrict__ pnrm, const double* __restrict__ pconv, int
 }
 
 // psi = ph * sum_{i<=order} c_i V_i   (tdse.py:475,394), c_i V_i = ceff_i * slab_i
-__global__ void __launch_bounds__(VEC_THREADS)
+__global__ void __launch_bounds__(VEC_THREADS, RMB_VEC_MINB)
 k_combine(cplx* const* __restrict__ slabs, long long ldv, long long n, const cplx* __restrict__ ceff,
           int tstride, const int* __restrict__ order, const cplx* __restrict__ ph,
           cplx* __restrict__ psi, long long ld, const int* __restrict__ pmap) {

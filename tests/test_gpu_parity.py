@@ -678,3 +678,44 @@ def test_linear_rotor_sliding_window_kernel():
     finally:
         del os.environ["RMB_FUSED"]
         clear_device_cache()
+
+
+def test_tiled_matvec_multi_tile_ctas_and_field_changes(monkeypatch):
+    """A CTA of the tiled matvec walks several state tiles of one item (RMB_MV2_TILES forces four): ragged last
+    unit, descriptor `nnz` refreshed when the surviving diagonals change between launches on the same operator,
+    and whole tiles that converge before their neighbours (states ordered by their Lanczos order)."""
+    monkeypatch.setenv("RMB_MV2_TILES", "4")
+    m = synth.h2o(5)
+    h0, dip, pol = m["h0"], m["dip"] * (-AUDIP), m["pol"] * (-0.5 * AUPOL)
+    N = h0._basis().N
+    # (a) matvec, 150 states (tiles of <= 32 states: units of four tiles and a ragged rest), three polarisations
+    x = random_states(150, N, seed=11)
+    o = oracle_of(dip)
+    for E in ([0, 0, 2e6], [1e6, 0, 2e6], [1e6, -3e6, 2e6], [0, 0, 1e6]):
+        dip.field(E)
+        o.field(E)
+        yo = np.array([port.flat_matvec(o, xi) for xi in x])
+        assert relerr(gpu_matvec(dip, x), yo) < 1e-13, E
+    # (b) propagation: strong-field and field-free-like states in separate tiles
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    rng = np.random.default_rng(5)
+    weak = np.zeros((70, N), dtype=np.complex128)
+    weak[np.arange(70), rng.integers(0, N, 70)] = 1e-4          # tiny norm: converges in fewer iterations
+    vecs0 = np.concatenate([random_states(80, N, seed=3), weak])
+    fields = [[2e7 * np.sin(0.5), 0.0, 2e7 * np.cos(0.5)]] * 2
+    od, op_ = oracle_of(dip), oracle_of(pol)
+    pol.field([0, 0, 1.5e9], thresh=1e1)
+    op_.field([0, 0, 1.5e9], thresh=1e1)
+
+    def build(E):
+        od.field(E)
+        return od.add(op_)
+    outs, orders = _oracle_run(h0, build, fields, vecs0.copy())
+    assert min(orders[0]) < max(orders[0])                      # tiles do finish at different iterations
+    vecs = vecs0.copy()
+    for i, E in enumerate(fields):
+        dip.field(E)
+        vecs, _ = tdse.update(dip + pol, vecs, H0=h0)
+        assert relerr(vecs, outs[i]) < TOL, i
+        assert list(tdse.last_orders) == orders[i], i
