@@ -428,7 +428,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             ds.nnz = 0;
                             ds.xrs = q.dk2 | 1;
                             ds.tab = q.tab;
-                            ds.pad1 = ds.pad2 = 0;
+                            ds.mreal = ds.pad2 = 0;
                             gdesc.push_back(ds);
                             xbe = std::max(xbe, it.nst * ds.nr * (q.dk2 | 1));
                         }
@@ -535,7 +535,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             ds.nr = xr.nr;
                             ds.xrs = q.dk2 | 1;
                             ds.tab = q.tab;
-                            ds.pad1 = ds.pad2 = 0;
+                            ds.mreal = ds.pad2 = 0;
                             gdesc.push_back(ds);
                         }
                         it.kt_total = (ktd + 1) & ~1;
@@ -790,8 +790,11 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     if ((rc = upload(&op->d_ent_tab, ent_tab.data(), ent_tab.size()))) return rc;
     if ((rc = upload(&op->d_tab_off, tab_off.data(), tab_off.size()))) return rc;
     if ((rc = upload(&op->d_tab_nd, tab_nd.data(), tab_nd.size()))) return rc;
-    if ((rc = upload<unsigned>(&op->d_tab_mask, nullptr, (size_t)op->ntab + 1))) return rc;
-    RMB_CUDA(cudaMemset(op->d_tab_mask, 0, ((size_t)op->ntab + 1) * sizeof(unsigned)));
+    // [0, ntab]: masks of the non-zero diagonals; [ntab + 1, 2 ntab + 1]: table has an MF entry with a non-zero
+    // imaginary part (fields in the XZ plane give real MF: the matvec then skips half of its z-stage)
+    if ((rc = upload<unsigned>(&op->d_tab_mask, nullptr, 2 * ((size_t)op->ntab + 1)))) return rc;
+    RMB_CUDA(cudaMemset(op->d_tab_mask, 0, 2 * ((size_t)op->ntab + 1) * sizeof(unsigned)));
+    op->d_tab_cplx = op->d_tab_mask + op->ntab + 1;
     RMB_CUDA(cudaMemset(op->d_ent_val, 0, std::max<size_t>(1, (size_t)op->nent) * sizeof(cplx)));
     if ((rc = upload(&op->d_kpool, kpool.data(), kpool.size()))) return rc;
     if ((rc = upload<int>(&op->d_flags, nullptr, (size_t)d->nparts + 1))) return rc;
@@ -835,12 +838,16 @@ int32_t rmb_operator_set_field(rmb_operator* op, int32_t part, const double* fpr
     const long long nent = ph.ent_end - ph.ent_begin;
     RMB_CUDA(cudaMemsetAsync(op->d_flags + 1 + part, 0, sizeof(int), st));
     if (ph.tab_end > ph.tab_begin)
+    {
         RMB_CUDA(cudaMemsetAsync(op->d_tab_mask + ph.tab_begin, 0, sizeof(unsigned) * (ph.tab_end - ph.tab_begin), st));
+        RMB_CUDA(cudaMemsetAsync(op->d_tab_cplx + ph.tab_begin, 0, sizeof(unsigned) * (ph.tab_end - ph.tab_begin), st));
+    }
     if (nent > 0) {
         const int nt = 256;
         k_field_contract<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ncart, ph.d_coef, fdev, fp, thresh, all_dropped, op->d_ent_val + ph.ent_begin,
-            op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, ph.ent_begin);
+            op->d_flags + 1 + part, op->d_ent_tab, op->d_tab_off, op->d_tab_nd, op->d_tab_mask, op->d_tab_cplx,
+            ph.ent_begin);
         k_compact_tables<<<(unsigned)((nent + nt - 1) / nt), nt, 0, st>>>(
             nent, ph.ent_begin, op->d_ent_val, op->d_ent_col, op->d_ent_tab, op->d_tab_off, op->d_tab_nd,
             op->d_tab_mask, op->d_ent_cent);
@@ -999,7 +1006,7 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             op->units_nstates = nstates;
         }
         if (op->nnz_dirty) {
-            k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask);
+            k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask, op->d_tab_cplx);
             op->nnz_dirty = false;
             op->n_launches++;
         }

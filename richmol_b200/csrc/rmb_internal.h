@@ -84,6 +84,7 @@ struct rmb_operator {
     int* d_tab_off = nullptr;        // [ntab] first entry of each table (int: nent < 2^31)
     int* d_tab_nd = nullptr;         // [ntab] ELL width
     unsigned* d_tab_mask = nullptr;  // [ntab] bit j set <=> diagonal slot j has a non-zero MF entry
+    unsigned* d_tab_cplx = nullptr;  // [ntab] non-zero <=> some MF entry of the table has a non-zero imaginary part (same allocation)
     int ntab = 0;
     double* d_kpool = nullptr;       // doubles, or interleaved complex if k_complex
     int* d_flags = nullptr;          // [0] mf non-empty flag (per set_field accumulates), [1..] scratch

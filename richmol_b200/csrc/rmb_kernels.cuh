@@ -73,7 +73,7 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
                                  cplx* __restrict__ val, int* __restrict__ nz_flag,
                                  const int* __restrict__ ent_tab, const int* __restrict__ tab_off,
                                  const int* __restrict__ tab_nd, unsigned* __restrict__ tab_mask,
-                                 long long ent_begin) {
+                                 unsigned* __restrict__ tab_cplx, long long ent_begin) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= nent) return;
     cplx acc = make_double2(0.0, 0.0);
@@ -95,6 +95,7 @@ __global__ void k_field_contract(long long nent, int ncart, const cplx* __restri
         const int t = ent_tab[ent_begin + e];
         const int slot = (int)((ent_begin + e - tab_off[t]) % tab_nd[t]);
         if (slot < 32) atomicOr(&tab_mask[t], 1u << slot);
+        if (acc.y != 0.0 && tab_cplx[t] == 0u) tab_cplx[t] = 1u;   // benign race: every writer stores 1
     }
 }
 

@@ -56,14 +56,19 @@ struct __align__(32) MfEntry { double re, im; int col; int pad[3]; };
 struct ProdS {
     long long ket_off;   // padded offset of the first staged ket row (c_lo already added)
     long long ent_off;   // first compacted entry of the MF table
-    int dk2, nnz, c_lo, nr, xrs, tab, pad1, pad2;
+    int dk2, nnz, c_lo, nr, xrs, tab, mreal, pad2;   // nnz, mreal (all surviving MF entries real): k_fill_nnz
 };
 
 // After a field update: surviving diagonals per (item, product) descriptor, so that the descriptors a CTA copies to
 // shared memory are complete (no dependent gather from the diagonal masks at CTA start)
-__global__ void k_fill_nnz(int n, ProdS* __restrict__ gdesc, const unsigned* __restrict__ tab_mask) {
+__global__ void k_fill_nnz(int n, ProdS* __restrict__ gdesc, const unsigned* __restrict__ tab_mask,
+                           const unsigned* __restrict__ tab_cplx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) gdesc[i].nnz = min(__popc(tab_mask[gdesc[i].tab]), MV2_NDMAX);
+    if (i < n) {
+        const int t = gdesc[i].tab;
+        gdesc[i].nnz = min(__popc(tab_mask[t]), MV2_NDMAX);
+        gdesc[i].mreal = tab_cplx[t] == 0u ? 1 : 0;
+    }
 }
 
 // ---- mbarrier / TMA (cp.async.bulk) helpers -----------------------------------------------------
@@ -154,7 +159,7 @@ __device__ __forceinline__ void mv2_load_krow(unsigned kt_byte, int k2, double (
 // Software pipeline over k2: the ket elements of column k2 + 1 (and, for few diagonals, row k2 + 1 of K^T) are
 // loaded into a second register set before the DFMAs of column k2, so the LDS latency of one column hides behind
 // the 4 * NC + 8 * NNZ DFMAs of the previous one (two consumer warps per scheduler are not enough to hide it).
-template <int NC, int NNZ, bool KC>
+template <int NC, int NNZ, bool KC, bool MR>
 __device__ __forceinline__ void mv2_inner(unsigned xa_byte, unsigned xb_byte, unsigned mfe_byte,
                                           int nrows, int c_lo, int xrs, unsigned kt_byte, int dk2,
                                           double2 (&accA)[NC], double2 (&accB)[NC]) {
@@ -201,10 +206,12 @@ __device__ __forceinline__ void mv2_inner(unsigned xa_byte, unsigned xb_byte, un
             zA.y = fma(mf[q].x, a[q].y, zA.y);
             zB.x = fma(mf[q].x, b[q].x, zB.x);
             zB.y = fma(mf[q].x, b[q].y, zB.y);
-            zA.x = fma(-mf[q].y, a[q].y, zA.x);
-            zA.y = fma(mf[q].y, a[q].x, zA.y);
-            zB.x = fma(-mf[q].y, b[q].y, zB.x);
-            zB.y = fma(mf[q].y, b[q].x, zB.y);
+            if (!MR) {                                       // MR: every surviving MF entry of the product is real
+                zA.x = fma(-mf[q].y, a[q].y, zA.x);
+                zA.y = fma(mf[q].y, a[q].x, zA.y);
+                zB.x = fma(-mf[q].y, b[q].y, zB.x);
+                zB.y = fma(mf[q].y, b[q].x, zB.y);
+            }
         }
         mv2_kstage<NC, KC>(krow, zA, zB, accA, accB);
         if (PX) {
@@ -279,14 +286,17 @@ __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __
                 const unsigned xb = xa + (unsigned)(nr * xrs) * 16u;   // an inactive partner reads stale data: never stored
                 const unsigned mfe = sm.mfe_b + (unsigned)stage * sm.mstride + (unsigned)rl * (unsigned)sizeof(MfEntry);
                 const unsigned ktp = sm.kt_b + (unsigned)ktbase * 8u;
-                switch (nnz) {
-                    case 0: break;
-                    case 1: mv2_inner<NC, 1, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 2: mv2_inner<NC, 2, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 3: mv2_inner<NC, 3, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    case 4: mv2_inner<NC, 4, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
-                    default: mv2_inner<NC, 5, KC>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break;
+#define RMB_NNZ(MRV)                                                                                              \
+                switch (nnz) {                                                                                     \
+                    case 0: break;                                                                                 \
+                    case 1: mv2_inner<NC, 1, KC, MRV>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break; \
+                    case 2: mv2_inner<NC, 2, KC, MRV>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break; \
+                    case 3: mv2_inner<NC, 3, KC, MRV>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break; \
+                    case 4: mv2_inner<NC, 4, KC, MRV>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break; \
+                    default: mv2_inner<NC, 5, KC, MRV>(xa, xb, mfe, nrows, c_lo, xrs, ktp, dk2, accA, accB); break; \
                 }
+                if (sp[ip].mreal) { RMB_NNZ(true) } else { RMB_NNZ(false) }
+#undef RMB_NNZ
             }
             ktbase += dk2 * NC * KW;
             __syncwarp();

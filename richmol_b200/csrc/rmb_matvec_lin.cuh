@@ -61,9 +61,11 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
               const unsigned* __restrict__ tab_mask, const MfEntry* __restrict__ cent,
               const double* __restrict__ kpool, int k_complex, const long long* __restrict__ val_off,
               LinEnt* __restrict__ flat, double2* __restrict__ val) {
-    __shared__ long long s_ent[ML_LMAX];
-    __shared__ double2 s_k[ML_LMAX];
-    __shared__ int s_L;
+    __shared__ long long s_ent[ML_LMAX];      // first compacted MF entry of the (product, diagonal) pair
+    __shared__ double2 s_k[ML_LMAX];          // its 1 x 1 K factor
+    __shared__ LinEnt s_le[ML_LMAX];          // its descriptor
+    __shared__ int s_map[ML_LMAX];            // pair -> merged entry
+    __shared__ int s_L, s_U;
     const int b = blockIdx.x, lane = threadIdx.x & 31;
     const int p0 = blk_begin[b], p1 = blk_begin[b + 1], dm1 = blk_dm[b];
     LinEnt* out = flat + (size_t)b * ML_FLAT;
@@ -100,31 +102,60 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
                             if (c >= 0) { e.doff = c - r; break; }
                         }
                         e.dm2 = blk_dm[ket];
-                        e.pad = 0;
-                        out[1 + base + q] = e;
+                        e.pad = ket;                       // ket block (two blocks never share a ring slot within W)
+                        s_le[base + q] = e;
                         s_ent[base + q] = e0;
                         s_k[base + q] = kv;
                     }
             }
             L += __shfl_sync(0xffffffffu, incl, 31);
         }
+        __syncwarp();
         if (lane == 0) {
+            // pairs that read the same ket block along the same diagonal (the rank-0 and rank-2 parts of a
+            // polarisability, operands of a sum that couple the same blocks) are merged into one entry: their
+            // values are added once per field update instead of once per state and launch
+            L = min(L, ML_LMAX);
+            int U = 0;
+            for (int j = 0; j < L; ++j) {
+                int u = 0;
+                for (; u < U; ++u)
+                    if (s_le[u].pad == s_le[j].pad && s_le[u].doff == s_le[j].doff) break;   // s_le[u], u < U <= j: already final
+                if (u == U) {
+                    const LinEnt e = s_le[j];
+                    s_le[U] = e;
+                    ++U;
+                }
+                s_map[j] = u;
+            }
             LinEnt h;
-            h.xbyte = (unsigned)min(L, ML_LMAX);
+            h.xbyte = (unsigned)U;
             h.doff = h.dm2 = h.pad = 0;
             out[0] = h;
-            s_L = min(L, ML_LMAX);
+            s_L = L;
+            s_U = U;
         }
     }
     __syncthreads();
-    const int L = s_L;
+    const int L = s_L, U = s_U;
+    for (int u = threadIdx.x; u < U; u += blockDim.x) {
+        LinEnt e = s_le[u];
+        e.pad = 0;
+        out[1 + u] = e;
+    }
     double2* vout = val + val_off[b];
-    for (int i = threadIdx.x; i < L * dm1; i += blockDim.x) {
-        const int j = i / dm1, r = i - j * dm1;
-        const MfEntry e = cent[s_ent[j] + r];
-        const double2 k = s_k[j];
-        vout[i] = e.col >= 0 ? make_double2(k.x * e.re - k.y * e.im, k.x * e.im + k.y * e.re)
-                             : make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < U * dm1; i += blockDim.x) {
+        const int u = i / dm1, r = i - u * dm1;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int j = u; j < L; ++j) {                        // members in list order (s_map[j] <= j)
+            if (s_map[j] != u) continue;
+            const MfEntry e = cent[s_ent[j] + r];
+            if (e.col < 0) continue;
+            const double2 k = s_k[j];
+            acc.x += k.x * e.re - k.y * e.im;
+            acc.y += k.x * e.im + k.y * e.re;
+        }
+        vout[i] = acc;
     }
 }
 
