@@ -474,9 +474,10 @@ def main():
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: H2O rigid rotor Watson-A Jmax=20 N={N}, same step as "
-                                   f"the GPU arm on a bounded sample of the ensemble",
-                       "hilbert_dim": N, "dt_ps": DT},
+            "config": {"workload": WORKLOAD_TEXT[args.workload].format(N=N, S=NSTATES),
+                       "states_per_gpu": NSTATES, "hilbert_dim": N, "dt_ps": DT,
+                       "parallelism": f"host processes x{cores}, rows of the ensemble split across them",
+                       "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
