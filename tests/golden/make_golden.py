@@ -54,6 +54,57 @@ def save(name, **arrays):
     print("wrote", name, {k: np.shape(v) for k, v in arrays.items()})
 
 
+def g4():
+    wpath = 'tests/benchmarks/data/h2o_rchm_files_TROVE/'
+    wstates = wpath + 'energies_j0_j40_MARVEL_HITRAN.rchm'
+
+    def filt(**kw):
+        ok = True
+        if 'J' in kw:
+            ok = ok and kw['J'] <= 2
+        if 'enr' in kw:
+            ok = ok and kw['enr'] <= 6000
+        return ok
+    H0 = quiet(r.trove.CarTensTrove, wstates, bra=filt, ket=filt)
+    mu = quiet(r.trove.CarTensTrove, wstates, wpath + 'matelem_MU_j<j1>_j<j2>.rchm', bra=filt, ket=filt)
+    save_cartens(os.path.join(HERE, "g4_h2o_trove_h0.npz"), CarTens.from_richmol(H0))
+    save_cartens(os.path.join(HERE, "g4_h2o_trove_mu.npz"), CarTens.from_richmol(mu))
+    mu = mu * (-1.0) * r.convert_units.Debye_x_Vm_to_invcm()
+    tdse = r.tdse.TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    vecs = tdse.init_state(H0, temp=40.0)
+    keep = np.sort(np.argsort(-np.linalg.norm(vecs, axis=1), kind="stable")[:24])
+    vecs = vecs[keep]                                # the 24 heaviest members (keeps the fixture small)
+    N = vecs.shape[1]
+    rng = np.random.default_rng(13)
+    x = rng.normal(size=N) + 1j * rng.normal(size=N)
+    fields = np.array([[3e7 * np.sin(0.4), 2e7 * np.sin(0.9 * i), 3e7 * np.cos(0.4) + 1e7 * np.cos(0.5 * i)]
+                       for i in range(6)])
+    outs, orders, mv = [], [], []
+    v = vecs.copy()
+    for i, E in enumerate(fields):
+        mu.field(E)
+        ORDERS.clear()
+        v, _ = tdse.update(mu, v, H0=H0)
+        orders.append(list(ORDERS))
+        outs.append(v.copy())
+        vd, ind = {}, 0
+        for J in mu.Jlist2:
+            vd[J] = {}
+            for sym in mu.symlist2[J]:
+                vd[J][sym] = x[ind: ind + mu.dim2[J][sym]]
+                ind += mu.dim2[J][sym]
+        y = mu.vec(vd)
+        mv.append(np.concatenate([y[J][sym] if J in y and sym in y[J] else np.zeros(mu.dim2[J][sym])
+                                  for J in mu.Jlist2 for sym in mu.symlist2[J]]))
+    save("g4_h2o_trove_run.npz", fields=fields, vecs0=vecs, outs=np.array(outs), orders=np.array(orders),
+         x=x, matvec=np.array(mv))
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "g4":      # only the newest fixture (the others are unchanged)
+    g4()
+    sys.exit(0)
+
 # ---------------------------------------------------------------------------------------------
 # g1: the reference's own unit test (tests/test_tdse.py:15-110): OCS, J even <= 30, m = 0
 # ---------------------------------------------------------------------------------------------
@@ -180,4 +231,11 @@ for i, E in enumerate(fields):
                               for J in H.Jlist2 for sym in H.symlist2[J]]))
 save("g3_camphor_run.npz", dc=np.array(dc), fields=fields, vecs0=vecs, outs=np.array(outs),
      orders=np.array(orders), x=x, matvec=np.array(mv), thresh=1e2)
+
+# ---------------------------------------------------------------------------------------------
+# g4: H2O rovibrational (TROVE) states and dipole, the fixture of tests/benchmarks/test_water_stark.py:
+#     J <= 2, enr <= 6000 cm^-1 (N = 280, real dense K blocks with dim_k up to 14, two to four symmetries per J);
+#     static tilted dc field + oscillating field along Y (complex MF, all m mixed), thermal ensemble
+# ---------------------------------------------------------------------------------------------
+g4()
 print("done")

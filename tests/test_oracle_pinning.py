@@ -80,6 +80,28 @@ def test_g3_camphor_lazy_sum():
         assert relerr(port.flat_matvec(H, g["x"]), g["matvec"][i]) < 1e-14
 
 
+def test_g4_h2o_trove_rovibrational_dipole():
+    """TROVE rovibrational H2O (the fixture of the reference's tests/benchmarks/test_water_stark.py): real dense K
+    blocks with dim_k up to 14, dipole in a field with a Y component (complex MF, every m mixed)."""
+    g = golden("g4_h2o_trove_run.npz")
+    h0, mu = oracle_of(load("g4_h2o_trove_h0.npz")), oracle_of(load("g4_h2o_trove_mu.npz"))
+    assert max(max(d.values()) for d in mu.dim_k2.values()) == 14
+    mu.mul(-1.0)
+    mu.mul(DEBYE)
+    full = port.init_state(h0, temp=40.0)
+    keep = np.sort(np.argsort(-np.linalg.norm(full, axis=1), kind="stable")[:24])
+    vecs = full[keep]
+    assert relerr(vecs, g["vecs0"]) < 1e-15
+    phase = port.h0_phase(h0, EXP_FAC)
+    for i, E in enumerate(g["fields"]):
+        mu.field(E)
+        o = []
+        vecs = port.update_step(mu, vecs, EXP_FAC, phase=phase, orders=o)
+        assert relerr(vecs, g["outs"][i]) < 1e-12
+        assert o == list(g["orders"][i])
+        assert relerr(port.flat_matvec(mu, g["x"]), g["matvec"][i]) < 1e-14
+
+
 @pytest.mark.reference
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
 def test_port_against_live_reference():

@@ -24,6 +24,7 @@ CASES = [
     ("h2o_h0", lambda: synth.h2o(3)["h0"], [0, 0, 1], None),
     ("camphor_mu", lambda: load("g3_camphor_mu.npz"), [1e6, 2e6, -1e6], None),
     ("camphor_alpha", lambda: load("g3_camphor_alpha.npz"), [1e9, 2e9, -1e9], 1e2),
+    ("h2o_trove_mu", lambda: load("g4_h2o_trove_mu.npz"), [3e6, -2e6, 1e6], None),
 ]
 
 
