@@ -1,13 +1,15 @@
-// K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, state tile).
+// K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, one or more state tiles).
 //
-// Thread mapping: one thread owns one row m1 of the bra block for TWO states and all (<= 16)
-// columns k1 of the tile; accumulators live in registers.  Per block product p
-//   * the ket rows the tile needs are staged in shared memory with cp.async (double buffered,
-//     coalesced 16-byte copies; row stride padded to an odd number of 16-byte words so that the
-//     row-strided reads below are bank-conflict free),
+// The CTA is two warpgroups.  Consumers: one thread owns one row m1 of the bra block for TWO states and all
+// (<= 12) columns k1 of the tile; accumulators live in registers.  Per block product p
+//   * the producer warpgroup stages the ket rows the tile needs and the surviving MF diagonals in shared memory
+//     with TMA bulk copies (cp.async.bulk) through a full / empty mbarrier ring of 2-6 stages; the internal
+//     vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous run per state and the
+//     row-strided reads below are bank-conflict free,
 //   * z = sum_j MF_p[m1, j] * X[col_j, k2] is formed on the fly in registers (zero MF diagonals are
-//     skipped: after the field contraction most of the (2w+1) diagonals vanish for polarised fields),
-//   * acc[k1] += K_p[k1, k2] * z with K_p^T broadcast from shared memory.
+//     skipped: after the field contraction most of the (2w+1) diagonals vanish for polarised fields; for real
+//     MF, i.e. fields in the XZ plane, half of the products are skipped as well),
+//   * acc[k1] += K_p[k1, k2] * z with the K_p^T row loaded once from shared memory for both states.
 // H(t) itself is never materialised: the kernel only sees the MF and K factors.
 #pragma once
 #include "rmb_internal.h"
@@ -52,7 +54,7 @@ constexpr int MV2_RED_BYTES = 4 * MV2_CONSUMERS * 8 + MV2_TILES_MAX * 4;   // <w
 struct __align__(32) MfEntry { double re, im; int col; int pad[3]; };
 
 // per-product descriptor staged in shared memory at CTA start
-// (built on the host; `nnz` is filled in by the producer warp from the field-dependent diagonal masks)
+// (built on the host; `nnz` and `mreal` are refreshed on the device after every field update: k_fill_nnz)
 struct ProdS {
     long long ket_off;   // padded offset of the first staged ket row (c_lo already added)
     long long ent_off;   // first compacted entry of the MF table
@@ -243,16 +245,9 @@ struct Mv2Smem {
     unsigned long long* setup;   // K^T image + descriptors have landed
 };
 
-// K2 (tiled version): y = sum_p (MF_p (x) K_p) x for one work unit = (bra-block tile, state tile).
-//
-//  * 8 consumer warps: one thread per (state, row m1) holding all (<= 12) columns k1 of the tile in
-//    registers; per block product p it forms z = sum_q MF_p[m1, q] * X[row_q, k2] on the fly (only the
-//    diagonals that survived the field contraction) and accumulates acc[k1] += K_p[k1, k2] * z with
-//    K_p^T broadcast from shared memory.  H(t) itself is never materialised.
-//  * 2 producer warps (states split even / odd): stage, per product and two products ahead of use, the ket rows of every state of
-//    the tile and the MF diagonals with TMA bulk copies (cp.async.bulk) completing on an mbarrier; the
-//    internal vectors store rows of (dim_k | 1) elements, so a tile's ket rows are one contiguous,
-//    bank-conflict-free run.
+// Consumer warpgroup (4 warps, 208 registers per thread after setmaxnreg): walks the state tiles of the unit; per
+// tile it zeroes the accumulators, consumes the products of the item in pipeline order (full wait -> mv2_inner ->
+// empty arrive) and runs the epilogue (scale, store, fused <w,V_k> partials through a consumer-only named barrier).
 template <int NC, bool KC>
 __device__ __forceinline__ void mv2_consumer(const Item2D& it, const double2* __restrict__ X,
                                              double2* __restrict__ Y, long long ldx, long long ldy, int nstates,
