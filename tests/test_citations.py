@@ -13,7 +13,10 @@ CITE = re.compile(r"(?<![\w/.])((?:[\w.-]+/)*[\w.-]+\.(?:py|pyf|f|ipynb|txt)):(\
 
 SOURCES = (["DESIGN.md", "INTEGRATION.md", "README.md"] + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
            + sorted(glob.glob(os.path.join(ROOT, "oracle", "*.py")))
-           + sorted(glob.glob(os.path.join(ROOT, "richmol_b200", "*.py"))))
+           + sorted(glob.glob(os.path.join(ROOT, "richmol_b200", "*.py")))
+           + sorted(glob.glob(os.path.join(ROOT, "richmol_b200", "csrc", "*.cu*")))
+           + sorted(glob.glob(os.path.join(ROOT, "richmol_b200", "csrc", "*.h")))
+           + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")])
 OWN = {os.path.basename(p) for p in glob.glob(os.path.join(ROOT, "**", "*.py"), recursive=True)}
 
 
