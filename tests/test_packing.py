@@ -121,3 +121,46 @@ def test_add_requires_same_basis():
     b.field([0, 0, 1.0])
     with pytest.raises(ValueError):
         a + b
+
+
+@pytest.mark.parametrize("what,E,thresh", [("pol", [0, 0, 2e9], 1e1), ("pol", [3e8, -2e8, 9e8], 1e3),
+                                           ("dip", [3e5, 0.0, 9e5], None), ("sum", None, None)])
+def test_linear_rotor_entry_lists_and_merge(what, E, thresh):
+    """The entry lists of the sliding-window matvec (k_lin_entries: one entry per surviving diagonal, pairs on the
+    same ket block and diagonal merged) evaluate to the oracle's matvec; merging removes entries whenever two
+    products couple the same blocks (rank 0 and rank 2 of a polarisability, operands of a sum)."""
+    m = synth.ocs(8)
+    if what == "sum":
+        dip, pol = m["dip"] * (-AUDIP), m["pol"] * (-0.5 * AUPOL)
+        dip.field([2e7 * np.sin(0.6), 0.0, 2e7 * np.cos(0.6)])
+        pol.field([0, 0, 2e9], thresh=1e1)
+        t = dip + pol
+        od, op_ = oracle_of(dip), oracle_of(pol)
+        od.field([2e7 * np.sin(0.6), 0.0, 2e7 * np.cos(0.6)])
+        op_.field([0, 0, 2e9], thresh=1e1)
+        o = od.add(op_)
+    else:
+        t = m[what]
+        t.field(E, thresh=thresh)
+        o = oracle_of(t)
+        o.field(E, thresh=thresh)
+    parts = t._parts()
+    basis = t._basis()
+    lists = packed_eval.lin_entry_lists(basis, [p for p, _, _ in parts], [fs for _, fs, _ in parts])
+    x = random_states(3, basis.N, seed=2)
+    yo = np.array([port.flat_matvec(o, xi) for xi in x])
+    assert relerr(packed_eval.lin_matvec(basis, lists, x), yo) < 1e-13
+    # no two entries of a bra block share (ket block, diagonal)
+    for ents in lists:
+        keys = [(b2, doff) for b2, doff, _ in ents]
+        assert len(keys) == len(set(keys))
+    if what in ("pol", "sum"):
+        # unmerged count = surviving diagonals over all products: strictly more than the merged lists hold
+        unmerged = 0
+        for part, fs, _ in parts:
+            val = packed_eval.contract_field(part, fs)
+            for p in range(len(part.pr_bra)):
+                tt = int(part.pr_table[p])
+                dm1, nd, e0 = int(basis.dm[int(part.pr_bra[p])]), int(part.tb_nd[tt]), int(part.tb_off[tt])
+                unmerged += int(np.any(val[e0:e0 + dm1 * nd].reshape(dm1, nd) != 0, axis=0).sum())
+        assert sum(len(e) for e in lists) < unmerged
