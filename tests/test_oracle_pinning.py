@@ -132,3 +132,83 @@ def test_port_against_live_reference():
         v_or = port.update_step(om, v_or, EXP_FAC, phase=phase)
         assert relerr(v_or, v_ref) < 1e-13
     assert relerr(om.tomat().toarray(), mu.tomat(form='full', repres='dense')) < 1e-15
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_host_mirror_time_grid_and_init_state_against_live_reference():
+    """richmol_b200.TDSE.time_grid / init_state (host side of the drop-in, richmol/tdse.py:146-262) against the
+    unmodified reference on tensors adopted with CarTens.from_richmol: grids for several (t_start, t_end, dt,
+    units), ensembles for T = 0, low T with the default and a tight partition threshold, and the error behaviour."""
+    from richmol_b200 import TDSE
+    from richmol_b200.field import CarTens
+    r = refshim.load()
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        path = 'tests/benchmarks/data/r-camphor_rchm_files/'
+        filt = lambda **kw: kw.get('J', 0) <= 3
+        with contextlib.redirect_stdout(io.StringIO()):
+            h0_ref = r.trove.CarTensTrove(path + 'camphor_energies_j0_j20.rchm', bra=filt, ket=filt)
+    finally:
+        os.chdir(cwd)
+    h0 = CarTens.from_richmol(h0_ref)
+    for kw in (dict(t_end=1, dt=0.01), dict(t_start=0.5, t_end=3.2, dt=0.07),
+               dict(t_start=0, t_end=2000, dt=10, t_units="fs"), dict(t_end=0.3, dt=0.01, t_units="ns")):
+        ours, ref = TDSE(**kw), r.tdse.TDSE(**kw)
+        assert np.array_equal(ours.time_grid(), ref.time_grid())
+        for a, b in zip(ours._time_grid, ref._time_grid):
+            assert np.array_equal(a, b)
+    ours, ref = TDSE(t_end=1, dt=0.01), r.tdse.TDSE(t_end=1, dt=0.01)
+    for kw in (dict(temp=0), dict(temp=None), dict(temp=1.5), dict(temp=5.0, thresh=1e-6), dict(temp=0.2, thresh=1e-1)):
+        a, b = ours.init_state(h0, **kw), ref.init_state(h0_ref, **kw)
+        assert a.shape == b.shape, kw
+        assert relerr(a, b) < 1e-15, kw
+    with pytest.raises(AssertionError):
+        ours.init_state(h0, temp=-1.0)
+    with pytest.raises(AssertionError):
+        ref.init_state(h0_ref, temp=-1.0)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_host_mirror_cartesian_matrices_against_live_reference():
+    """CarTens.tomat(cart=...) (richmol/field.py:449-569: sum_irrep kron(M_cart, K), block and full form) and the
+    scalar algebra of the host mirror (mul / __mul__ / __rmul__, field.py:932-948, 1248-1301) against the reference,
+    on the camphor dipole and polarisability (complex M, dense K, four symmetries)."""
+    from richmol_b200.field import CarTens
+    r = refshim.load()
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        path = 'tests/benchmarks/data/r-camphor_rchm_files/'
+        filt = lambda **kw: kw.get('J', 0) <= 2
+        with contextlib.redirect_stdout(io.StringIO()):
+            refs = [r.trove.CarTensTrove(path + 'camphor_energies_j0_j20.rchm',
+                                         path + f'camphor_matelem_{nm}_j<j1>_j<j2>.rchm', bra=filt, ket=filt)
+                    for nm in ('mu', 'alpha')]
+    finally:
+        os.chdir(cwd)
+    for ref in refs:
+        ours = CarTens.from_richmol(ref)
+        assert list(ours.cart) == list(ref.cart) and ours.rank == ref.rank
+        for scale in (None, -0.5, 2.0 - 0.25j):
+            a, b = ours, ref
+            if scale is not None:
+                a, b = ours * scale, ref * scale
+                a2, b2 = scale * ours, scale * ref
+            for cart in ref.cart:
+                fa, fb = a.tomat(form='full', cart=cart), b.tomat(form='full', cart=cart)
+                assert relerr(fa.toarray(), fb.toarray()) < 1e-15, (cart, scale)
+                if scale is not None:
+                    assert relerr(a2.tomat(form='full', cart=cart).toarray(), fb.toarray()) < 1e-15
+            blk_a, blk_b = a.tomat(form='block', cart=ref.cart[0]), b.tomat(form='block', cart=ref.cart[0])
+            assert blk_a.keys() == blk_b.keys()
+            for Jp in blk_b:
+                assert blk_a[Jp].keys() == blk_b[Jp].keys()
+                for sp_ in blk_b[Jp]:
+                    assert relerr(blk_a[Jp][sp_].toarray(), blk_b[Jp][sp_].toarray()) < 1e-15
+        with pytest.raises(ValueError):
+            ours.tomat(cart="nope")
+        with pytest.raises(ValueError):
+            ref.tomat(cart="nope")
