@@ -132,6 +132,13 @@ def test_port_against_live_reference():
         v_or = port.update_step(om, v_or, EXP_FAC, phase=phase)
         assert relerr(v_or, v_ref) < 1e-13
     assert relerr(om.tomat().toarray(), mu.tomat(form='full', repres='dense')) < 1e-15
+    # field-dressed initial states (tdse.py:231-233: dense eigh of h0 + V), as in examples/ocs_mixed_field.py
+    E = [2e7, -1e7, 3e7]
+    mu.field(E)
+    om.field(E)
+    d_ref = tdse.init_state(h0 + mu, temp=3.0)
+    d_or = port.init_state(oh.add(om), temp=3.0)
+    assert d_or.shape == d_ref.shape and relerr(d_or, d_ref) < 1e-13
 
 
 @pytest.mark.reference
