@@ -132,6 +132,20 @@ def test_port_against_live_reference():
         v_or = port.update_step(om, v_or, EXP_FAC, phase=phase)
         assert relerr(v_or, v_ref) < 1e-13
     assert relerr(om.tomat().toarray(), mu.tomat(form='full', repres='dense')) < 1e-15
+    # the `tol` keyword (tdse.py:301-306): looser stop rule, same vectors and fewer iterations on both sides;
+    # reaching `maxorder` raises the reference's ValueError (tdse.py:480-484)
+    for tol in (1e-6, 1e-10, 1):
+        a, _ = tdse.update(mu, v_ref, H0=h0, tol=tol)
+        b = port.update_step(om, v_or, EXP_FAC, phase=phase, tol=tol)
+        assert relerr(b, a) < 1e-13, tol
+    with pytest.raises(AssertionError):
+        tdse.update(mu, v_ref, H0=h0, tol=0)
+    mu.field([5e10, 0, 5e10])
+    om.field([5e10, 0, 5e10])
+    with pytest.raises(ValueError, match="Lanczos reached maximum order"):
+        r.tdse._expmv_lanczos(v_ref[0], EXP_FAC, lambda v: port.flat_matvec(om, v), maxorder=4)
+    with pytest.raises(ValueError, match="Lanczos reached maximum order"):
+        port.expmv_lanczos(v_or[0], EXP_FAC, lambda v: port.flat_matvec(om, v), maxorder=4)
     # field-dressed initial states (tdse.py:231-233: dense eigh of h0 + V), as in examples/ocs_mixed_field.py
     E = [2e7, -1e7, 3e7]
     mu.field(E)
