@@ -233,3 +233,34 @@ def test_host_mirror_cartesian_matrices_against_live_reference():
             ours.tomat(cart="nope")
         with pytest.raises(ValueError):
             ref.tomat(cart="nope")
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_port_lanczos_against_the_reference_function():
+    """oracle.port.expmv_lanczos against richmol.tdse._expmv_lanczos itself (tdse.py:417-486) with the same matvec
+    callable: the exact zero-beta branch (a state the operator does not couple: Gram-Schmidt of the all-ones vector,
+    :459-465), an exact eigenvector (beta ~ 1e-16), unnormalised and complex start vectors, several `fac`."""
+    r = refshim.load()
+    rng = np.random.default_rng(3)
+    n = 12
+    A = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    A = (A + A.conj().T) / 2
+    H = np.zeros((n + 1, n + 1), dtype=complex)
+    H[1:, 1:] = A
+    mv = lambda v: H @ v
+    _, U = np.linalg.eigh(A)
+    eig = np.zeros(n + 1, dtype=complex)
+    eig[1:] = U[:, 0]
+    starts = {"decoupled": np.eye(n + 1)[0].astype(complex), "eigenvector": eig,
+              "random": 0.3 * (rng.normal(size=n + 1) + 1j * rng.normal(size=n + 1)),
+              "mixed": np.concatenate([[2.0], 1e-3 * U[:, 1]]).astype(complex)}
+    for name, v in starts.items():
+        for fac in (EXP_FAC, 10 * EXP_FAC, -0.05j, 0.02 - 0.01j):
+            info = []
+            a = r.tdse._expmv_lanczos(v.copy(), fac, mv)
+            b = port.expmv_lanczos(v.copy(), fac, mv, info=info)
+            assert relerr(b, a) < 1e-14, (name, fac)
+    info = []
+    port.expmv_lanczos(starts["decoupled"].copy(), EXP_FAC, mv, info=info)
+    assert info == [1]
