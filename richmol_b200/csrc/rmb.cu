@@ -731,7 +731,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 if ((rc = upload(&op->d_prod_ket, h_prod_ket.data(), h_prod_ket.size()))) return rc;
                 std::vector<LinBlk> lb(d->nblocks);
                 int chunk0 = 0, ubase = 0;
-                const int G = op->lin_T / (op->lin_T <= ML_TS ? op->lin_T / 2 : ML_TS);
+                op->lin_g1 = getenv("RMB_LIN_G1") && atoi(getenv("RMB_LIN_G1")) == 1;     // soak / sanitizer runs only
+                const int G = op->lin_g1 ? 1 : op->lin_T / (op->lin_T <= ML_TS ? op->lin_T / 2 : ML_TS);
                 for (int b = 0; b < d->nblocks; ++b) {
                     const int nch = (d->blk_dm[b] + 31) / 32;
                     lb[b].off = poff[b];
@@ -752,6 +753,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 if (!g_lin_attr) {
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     g_lin_attr = true;
                 }
                 op->h_bra_begin = bra_begin;
@@ -955,7 +958,13 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             op->n_launches++;
         }
         const unsigned grid = (unsigned)((nstates + T - 1) / T);
-        if (T == 8)
+        if (op->lin_g1 && T == 8)
+            k_matvec_lin<8, true><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                          ep.scale_stride, ep.pdot, ep.npart);
+        else if (op->lin_g1)
+            k_matvec_lin<4, true><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                          ep.scale_stride, ep.pdot, ep.npart);
+        else if (T == 8)
             k_matvec_lin<8><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
                                                                     ep.scale_stride, ep.pdot, ep.npart);
         else
@@ -1574,14 +1583,14 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
         k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
                                                     op->d_pmap);
         op->n_launches++;
-        if (fused_dot(op) || op->lin_ok) {
+        const bool lin = op->lin_ok && b >= 4 * op->lin_T;      // same routing as lanczos_batch
+        if (lin || fused_dot(op)) {
             // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
             // the product vector itself is never written
             MvEpilogue ep;
             ep.pdot = op->d_pdot;
-            ep.use_lin = op->lin_ok && b >= 4 * op->lin_T;
+            ep.use_lin = lin;
             ep.npart = ep.use_lin ? op->lin_npart : dot_parts(op);
-            if (!ep.use_lin && !fused_dot(op)) { set_error("internal: unfused expectation"); return RMB_ERR_INVALID; }
             if ((rc = launch_matvec(op, op->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;
@@ -1642,6 +1651,54 @@ int32_t rmb_operator_work(rmb_operator* op, double* flops_per_state, double* op_
     }
     if (flops_per_state) *flops_per_state = fl;
     if (op_bytes) *op_bytes = by;
+    return RMB_OK;
+}
+
+int32_t rmb_operator_info(const rmb_operator* op, int64_t* out8) {
+    if (!op || !out8) return RMB_ERR_INVALID;
+    out8[0] = op->nitems2;
+    out8[1] = op->nitemsG;
+    out8[2] = op->nitems;
+    out8[3] = op->lin_ok ? op->lin_T : 0;
+    out8[4] = op->fused_ok ? 1 : 0;
+    out8[5] = op->dk_max;
+    out8[6] = op->np;
+    out8[7] = op->nprod;
+    return RMB_OK;
+}
+
+int32_t rmb_fp64_peak(double* dfma_tflops, double* dmma_tflops, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    RMB_CUDA(cudaGetDevice(&dev));
+    RMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int threads = 256, blocks = sms * 8, iters = 20000;
+    double* out = nullptr;
+    RMB_CUDA(cudaMalloc((void**)&out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    RMB_CUDA(cudaEventCreate(&e0));
+    RMB_CUDA(cudaEventCreate(&e1));
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 4; ++rep) {          // rep 0 warms up
+            RMB_CUDA(cudaEventRecord(e0, st));
+            if (which == 0) k_peak_dfma<<<blocks, threads, 0, st>>>(out, rep ? iters : 100);
+            else k_peak_dmma<<<blocks, threads, 0, st>>>(out, rep ? iters : 100);
+            RMB_CUDA(cudaEventRecord(e1, st));
+            RMB_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            RMB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (!rep) continue;
+            const double fl = which == 0 ? 2.0 * 8 * iters * (double)blocks * threads
+                                         : 2.0 * 8 * 8 * 4 * 4 * iters * (double)blocks * (threads / 32);
+            best[which] = std::max(best[which], fl / ms * 1e-9);
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    RMB_CUDA(cudaGetLastError());
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
     return RMB_OK;
 }
 

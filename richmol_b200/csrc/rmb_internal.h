@@ -131,6 +131,7 @@ struct rmb_operator {
 
     // ---- sliding-window matvec for linear rotors (rmb_matvec_lin.cuh)
     bool lin_ok = false;
+    bool lin_g1 = false;         // RMB_LIN_G1=1: single-state-group instantiation (soak / sanitizer runs only)
     int lin_W = 0, lin_T = 0, lin_dm_max = 0, lin_NS = 0, lin_npart = 0;
     size_t lin_smem = 0;
     bool lin_flat_dirty = true;      // entry lists must be rebuilt (field changed)

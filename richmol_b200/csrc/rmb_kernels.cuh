@@ -664,4 +664,30 @@ __global__ void k_populations(const cplx* __restrict__ psi, long long nstates, l
     pop[x] = acc;
 }
 
+// ---- FP64 roofline denominators (rmb_fp64_peak): register-resident DFMA and DMMA loops
+__global__ void k_peak_dfma(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void k_peak_dmma(double* out, int iters) {
+    double c0[4][2] = {{0}};
+    const double a = threadIdx.x * 1e-9, b = 1.0000001;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[j][0]), "+d"(c0[j][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int j = 0; j < 4; ++j) s += c0[j][0] + c0[j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace rmb

@@ -163,12 +163,14 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
 // thread; per (entry, state) the inner loop is one LDS.128 and four DFMA.  Units are dealt round-robin to the
 // compute warps across blocks; warps only synchronise through mbarriers (`full`: ket block landed, `efull`:
 // entries landed, `done`: bra block consumed by a warp).
-template <int T>
+// G1 = true: the single-state-group instantiation (one warp per 32-row chunk and all T states), built for the
+// soak / sanitizer runs of tools/lin_soak.py only (RMB_LIN_G1=1); the product path uses two state groups.
+template <int T, bool G1 = false>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict__ Y, long long ldx,
              long long ldy, int nstates, const int* __restrict__ active, const double* __restrict__ scale,
              int scale_stride, double2* __restrict__ pdot, int npart) {
-    constexpr int TS = T <= ML_TS ? T / 2 : ML_TS;            // states per thread (always two state groups)
+    constexpr int TS = G1 ? T : (T <= ML_TS ? T / 2 : ML_TS); // states per thread (two state groups unless G1)
     constexpr int G = T / TS;                                 // state groups
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NS = a.NS;

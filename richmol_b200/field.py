@@ -164,11 +164,14 @@ class CarTens:
                 v = getattr(obj, a)
                 depth = {"kmat": 3, "mmat": 4}.get(a, 0)
                 setattr(self, a, _copy_nested(v, depth) if depth else copy.copy(v))
-        if not hasattr(self, "mmat") and hasattr(obj, "mfmat"):
-            self._static_mf = _copy_nested(obj.mfmat, 3)
-            self._fstate = FieldState([1.0], None, False)
-        elif hasattr(obj, "mfmat") and hasattr(obj, "_rmb_field"):
+        if hasattr(obj, "mfmat") and hasattr(obj, "mmat") and hasattr(obj, "_rmb_field"):
             self.field(*obj._rmb_field)
+        elif hasattr(obj, "mfmat"):
+            # a frozen sum, or a reference tensor after its own `H.field(...)` (the canonical loop of
+            # examples/ocs_alignment.py:93-96): the contracted `mfmat` IS the operator; an empty one (every
+            # field product screened out, field.py:1107-1112) makes the Krylov part skippable (tdse.py:377)
+            self._static_mf = _copy_nested(obj.mfmat, 3)
+            self._fstate = FieldState([1.0], None, len(obj.mfmat) == 0)
         return self
 
     # -- internals -------------------------------------------------------------------------------
@@ -245,8 +248,12 @@ class CarTens:
 
         The contraction MF = sum_cart (prod E_c) M_cart runs on the GPU the next time the operator is
         applied; product screening (|prod| < thresh dropped, also the "0" product) is done here."""
-        if "_sum_parts" in self.__dict__ or "_static_mf" in self.__dict__:
+        if "_sum_parts" in self.__dict__ or ("_static_mf" in self.__dict__ and "mmat" not in self.__dict__):
             raise AttributeError("'CarTens' object has no attribute 'mmat'")   # field.py:1115 on a sum
+        if "_static_mf" in self.__dict__:
+            # adopted together with a contracted mfmat: a new field replaces it (field.py:1107)
+            self.__dict__.pop("_static_mf")
+            self.__dict__.pop("_packed", None)
         fprod, all_dropped = field_products(self.cart, field, thresh)
         self.__dict__["_fstate"] = FieldState(fprod, thresh, all_dropped)
         self.__dict__["_rmb_field"] = (list(field[:3]), thresh)
@@ -373,6 +380,8 @@ class CarTens:
                 res.__dict__[k] = _copy_nested(v, 4)
             elif k == "_mfmat_cache":
                 continue
+            elif k in ("_packed", "_basis_cache"):
+                res.__dict__[k] = v      # immutable: shared, so clones map to the same device operator
             else:
                 res.__dict__[k] = copy.copy(v)
         return res

@@ -164,7 +164,15 @@ class PackedPart:
         return self
 
     def scaled(self, factor):
-        """Same tables with every K multiplied by `factor` (CarTens.mul, field.py:932-948)."""
+        """Same tables with every K multiplied by `factor` (CarTens.mul, field.py:932-948).
+        Memoised per factor: the per-step pattern `H = -0.5 * pol * E` of the reference's examples
+        then maps to ONE packed part (and so to one device operator, which is keyed by part identity)
+        instead of a new table upload every step."""
+        memo = self.__dict__.setdefault("_scaled_memo", {})
+        fkey = complex(factor)
+        hit = memo.get(fkey)
+        if hit is not None:
+            return hit
         new = PackedPart()
         new.__dict__.update(self.__dict__)
         kp = self.kpool * factor
@@ -174,6 +182,10 @@ class PackedPart:
         else:
             new.kpool = np.ascontiguousarray(kp.real, dtype=np.float64)
             new.k_is_complex = False
+        new.__dict__["_scaled_memo"] = {}
+        if len(memo) >= 8:
+            memo.pop(next(iter(memo)))
+        memo[fkey] = new
         return new
 
     # -- helpers -----------------------------------------------------------------------------

@@ -344,3 +344,69 @@ def h2s(Jmax, **kw):
     st = asymmetric_rotor(*H2S_ABC, Jmax, **kw)
     return dict(states=st, h0=hamiltonian_tensor(st), pol=lab_tensor(H2S_POL, st),
                 cos2=lab_tensor("cos2theta", st))
+
+
+def trove_style(Jmax, nk=25, seed=0, kscale=1e-2, Jmin=0):
+    """Synthetic asymmetric top in the shape of a TROVE rovibrational database (BASELINE config 5; the
+    structure follows the H2O fixture of the reference, tests/benchmarks/data/h2o_rchm_files_TROVE/ read by
+    richmol/trove.py:130-191): for every J four C2v-like symmetries 'A1', 'A2', 'B1', 'B2' with `nk`
+    rovibrational states each, a rank-1 (dipole) tensor whose M factors are the exact 3j expressions of
+    `lab_tensor` and whose K factors are dense real random blocks (`default_rng(seed)`, normal * kscale).
+    The selection rule couples A1<->A2 and B1<->B2 for J' - J = 0, +-1; K(J2,J1) is chosen as
+    +-K(J1,J2)^T with the sign that makes the field-dressed operator Hermitian.
+    Returns dict(states, h0, dip)."""
+    rng = np.random.default_rng(seed)
+    syms = ["A1", "A2", "B1", "B2"]
+    partner = {"A1": "A2", "A2": "A1", "B1": "B2", "B2": "B1"}
+    st = RotorStates()
+    for J in range(Jmin, Jmax + 1):
+        Jf = float(J)
+        st.Jlist.append(Jf)
+        st.sym[Jf] = list(syms)
+        st.mlist[Jf] = list(range(-J, J + 1))
+        st.enr[Jf], st.coef[Jf], st.label[Jf] = {}, {}, {}
+        for i, s in enumerate(syms):
+            st.enr[Jf][s] = 9.5 * J * (J + 1) + 1.0 * i + np.sort(rng.uniform(0.0, 4000.0, size=nk))
+            st.coef[Jf][s] = np.zeros((2 * J + 1, nk))          # only the shape (dim_k) is used
+            st.label[Jf][s] = [f"{J} {s} {v}" for v in range(nk)]
+    h0 = hamiltonian_tensor(st)
+    us, ux, os_, cart = cart_to_spher(1)
+    t = CarTens()
+    t.rank, t.cart, t.os = 1, cart, os_
+    _basis_attrs(t, st)
+    t.kmat, t.mmat = {}, {}
+    mtab = {}
+    for J1 in st.Jlist:
+        for J2 in st.Jlist:
+            j1, j2 = int(J1), int(J2)
+            if abs(j1 - j2) > 1 or j1 + j2 < 1:
+                continue
+            m1 = np.array(st.mlist[J1])[:, None]
+            m2 = np.array(st.mlist[J2])[None, :]
+            mcart = np.zeros((3,) + np.broadcast(m1, m2).shape, dtype=np.complex128)
+            for i, (w, s) in enumerate(os_):
+                mcart += ux[:, i][:, None, None] * wigner3j(j2, 1, j1, m2, s, -m1)[None]
+            mcart *= math.sqrt((2 * j1 + 1) * (2 * j2 + 1)) * (1.0 - 2.0 * (np.abs(m1) % 2))
+            mcart[np.abs(mcart) < _EPS] = 0
+            mtab[(J1, J2)] = mcart
+    for (J1, J2), mc in mtab.items():
+        if J1 > J2:
+            continue
+        # M_c(J2,J1) = sgn * M_c(J1,J2)^+ for every Cartesian component: K(J2,J1) = sgn * K(J1,J2)^T
+        back = mtab[(J2, J1)]
+        ref = np.conj(np.transpose(mc, (0, 2, 1)))
+        i = np.unravel_index(np.argmax(np.abs(ref)), ref.shape)
+        sgn = float(np.sign((back[i] / ref[i]).real))
+        assert np.allclose(back, sgn * ref, atol=1e-12)
+        mm = {c: csr_matrix(mc[ic]) for ic, c in enumerate(cart) if np.any(mc[ic] != 0)}
+        mmb = {c: csr_matrix(back[ic]) for ic, c in enumerate(cart) if np.any(back[ic] != 0)}
+        for s1 in syms:
+            s2 = partner[s1]
+            if J1 == J2 and s1 > s2:
+                continue
+            k = rng.normal(size=(nk, nk)) * kscale
+            t.kmat.setdefault((J1, J2), {})[(s1, s2)] = {1: csr_matrix(k)}
+            t.mmat.setdefault((J1, J2), {})[(s1, s2)] = {1: dict(mm)}
+            t.kmat.setdefault((J2, J1), {})[(s2, s1)] = {1: csr_matrix(sgn * k.T)}
+            t.mmat.setdefault((J2, J1), {})[(s2, s1)] = {1: dict(mmb)}
+    return dict(states=st, h0=h0, dip=t)

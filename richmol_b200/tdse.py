@@ -14,7 +14,6 @@ reference's, so per-state iteration counts match.
     stays resident in HBM between steps (pass `inplace=True` to update it in place).
 """
 import functools
-import warnings
 
 import numpy as np
 import scipy.constants as const
@@ -43,12 +42,13 @@ def _as_cartens(obj, cache):
         return obj
     if hasattr(obj, "kmat") and (hasattr(obj, "mmat") or hasattr(obj, "mfmat")):
         # a richmol.field.CarTens: adopt it (static operators are re-packed when their mfmat changes)
-        key = (id(obj), id(getattr(obj, "mfmat", None)), id(obj.kmat))
+        # the entry keeps `obj` and the dictionaries alive, so their ids cannot be recycled while it is live
+        mf, km = getattr(obj, "mfmat", None), obj.kmat
         hit = cache.get("adopt")
-        if hit is None or hit[0] != key:
-            hit = (key, CarTens.from_richmol(obj))
+        if hit is None or hit[0] is not obj or hit[1] is not mf or hit[2] is not km:
+            hit = (obj, mf, km, CarTens.from_richmol(obj))
             cache["adopt"] = hit
-        return hit[1]
+        return hit[3]
     raise TypeError(f"bad operator type: '{type(obj)}'")
 
 
@@ -220,8 +220,8 @@ class TDSE():
         """Propagates vectors by one time-step (richmol/tdse.py:265-414).
 
         Kwargs: `H0` (field-free Hamiltonian -> split-operator step), `matvec_lib` (accepted,
-        ignored: the CUDA path is the only one), `propag` ('internal'; 'external' is served by the
-        same Lanczos kernel), `tol` (default 1e-15), and the extensions
+        ignored: the CUDA path is the only one), `propag` ('internal'; 'external' = Expokit raises
+        NotImplementedError), `tol` (default 1e-15), and the extensions
         `inplace` (CUDA tensors only), `out` (numpy result buffer, e.g. pinned memory) and `expect`
         (numpy path: list of observables whose per-state expectation values of the propagated states are
         left in `tdse.last_expect[(iobs, istate)]`, computed on the device before the download)."""
@@ -240,10 +240,13 @@ class TDSE():
                 f"propagator 'propag' has bad type: '{type(kwargs['propag'])}', (must be 'str')"
             assert (kwargs['propag'] in ['external', 'internal']), \
                 f"propagator 'propag' has bad value: '{kwargs['propag']}', (use 'external', 'internal')"
-            if kwargs['propag'] == 'external' and not self._cache.get("warned_external"):
-                warnings.warn("propag='external' (Expokit zhexpv) is served by the Lanczos kernel of "
-                              "propag='internal' in richmol_b200", stacklevel=3)
-                self._cache["warned_external"] = True
+            if kwargs['propag'] == 'external':
+                # richmol/tdse.py:385-392,405-412 -> pyexpokit.zhexpv (Fortran ZHEXPV: m = 12, adaptive
+                # sub-steps, Pade(6,6)).  A different algorithm with different iterates; answering it with the
+                # internal Lanczos would silently return another result under the reference's own keyword.
+                raise NotImplementedError(
+                    "propag='external' (Expokit ZHEXPV) is not provided by richmol_b200; use the default "
+                    "propag='internal' (richmol's in-house Lanczos, reproduced to 1e-10)")
 
         if 'tol' in kwargs:
             assert (type(kwargs['tol']) in [int, float]), \
@@ -330,7 +333,8 @@ class TDSE():
         for O in obs:
             if not O._has_field() and getattr(O, "cart", [None])[0] == "0":
                 O.field([0, 0, 1])
-        handles = (C.c_void_p * max(1, len(obs)))(*[O._device(stream).handle for O in obs])
+        obs_ops = [O._device(stream) for O in obs]      # referenced until the call returns (LRU eviction)
+        handles = (C.c_void_p * max(1, len(obs)))(*[o.handle for o in obs_ops])
         expv = np.zeros((len(obs), nst), dtype=np.complex128)
         status = lib.rmb_propagate_step_host_obs(
             op.handle, vin.ctypes.data, vout.ctypes.data, nst, N, exp_fac.real, exp_fac.imag,
@@ -427,7 +431,8 @@ class TDSE():
         for O in obs:
             if not O._has_field() and getattr(O, "cart", [None])[0] == "0":
                 O.field([0, 0, 1])
-        handles = (C.c_void_p * max(1, len(obs)))(*[O._device(stream).handle for O in obs])
+        obs_ops = [O._device(stream) for O in obs]      # referenced until the call returns (LRU eviction)
+        handles = (C.c_void_p * max(1, len(obs)))(*[o.handle for o in obs_ops])
         nst = work.shape[0]
         nout = nsteps // max(1, every)
         expv = torch.zeros((max(nout, 1), max(len(obs), 1), nst), dtype=torch.complex128, device=work.device)
