@@ -171,7 +171,7 @@ int32_t rmb_operator_work(rmb_operator* op, double* flops_per_state, double* op_
  * the number of launches it covers; enabling timing serialises with event syncs at query time only */
 int32_t rmb_matvec_timing(rmb_operator* op, int32_t enable, double* ms_out, int64_t* launches_out);
 /* how the matvec of this operator is routed: out8 = { tiled items (k_matvec_tiled), DMMA items
- * (k_matvec_gemm), scalar items (k_matvec_scalar), sliding-window kernel usable (k_matvec_lin),
+ * (k_matvec_dmma), scalar items (k_matvec_scalar), sliding-window kernel usable (k_matvec_lin),
  * single-launch step usable (k_lanczos_fused), max dim_k, padded dimension, products }            */
 int32_t rmb_operator_info(const rmb_operator* op, int64_t* out8);
 /* FP64 roofline denominators measured on the current device (MEASURED_PEAKS.json has no FP64 entry):

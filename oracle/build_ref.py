@@ -3,9 +3,11 @@
 The reference (CFEL-CMI/richmol) is pure Python on the TDSE path, so "building" it means
 byte-compiling the handful of modules the path imports, from the sources where they lie under
 /root/reference, into `oracle/_ref/richmol/*.pyc` (sourceless layout: Python imports `X.pyc` next
-to a missing `X.py`).  Only compiled outputs are written -- no reference source is copied into
-this repository -- and `oracle/_ref/` is git-ignored (not gpurun-ignored), so the byte code travels
-to the GPU box where /root/reference does not exist.  There `oracle/refshim.py` imports it with
+to a missing `X.py`) and packing those into `oracle/_ref/richmol_ref.zip` (zipimport reads sourceless
+byte code from an archive; the snapshot that travels to the GPU box drops loose `*.pyc` files).  Only
+compiled outputs are written -- no reference source is copied into this repository -- and
+`oracle/_ref/` is git-ignored (not gpurun-ignored), so the byte code travels to the GPU box where
+/root/reference does not exist.  There `oracle/refshim.py` imports it with
 the stub modules of SURVEY.md Appendix B, and `bench.py --impl reference` / `cpu_baseline` time the
 reference's own `CarTens.field` + `TDSE.update` (cpu_baseline.kind = "reference").
 
@@ -38,6 +40,10 @@ def build(quiet=True):
         # unchecked-hash pycs: valid without the source file and independent of its mtime
         py_compile.compile(src, cfile=dst, dfile=f"richmol/{m}.py", doraise=True, quiet=2 if quiet else 0,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    import zipfile
+    with zipfile.ZipFile(os.path.join(OUT, "richmol_ref.zip"), "w", zipfile.ZIP_STORED) as z:
+        for m in MODULES:
+            z.write(os.path.join(dst_dir, m + ".pyc"), f"richmol/{m}.pyc")
     with open(os.path.join(OUT, "VERSION"), "w") as f:
         f.write(f"byte code of {', '.join(m + '.py' for m in MODULES)} from {src_dir}, "
                 f"python {sys.version.split()[0]}\n")

@@ -16,7 +16,7 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("RICHMOL_REFERENCE", "/root/reference")
-BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "richmol_ref.zip")
 
 
 def available():
@@ -26,7 +26,7 @@ def available():
 
 def built():
     """The byte-compiled reference modules of `oracle/build_ref.py` are present."""
-    return os.path.isfile(os.path.join(BUILT_ROOT, "richmol", "tdse.pyc"))
+    return os.path.isfile(BUILT_ROOT)
 
 
 def root():

@@ -11,7 +11,7 @@
 #include "rmb_kernels.cuh"
 #include "rmb_matvec.cuh"
 #include "rmb_fused.cuh"
-#include "rmb_matvec_gemm.cuh"
+#include "rmb_matvec_dmma.cuh"
 #include "rmb_matvec_lin.cuh"
 
 namespace rmb {
@@ -339,13 +339,9 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         return item_smem_st(xbuf_elems, nrows, kt_doubles, nprod, MV2_STAGES);
     };
     const char* force = getenv("RMB_MATVEC");
-    auto itemG_smem = [](size_t xbuf_elems, int nrows, int ldk) {
-        return xbuf_elems * 16 + (size_t)MV2_NDMAX * nrows * sizeof(MfEntry) + (size_t)4 * MG_M * MG_LDZ * 8 +
-               (size_t)2 * MG_KCH * ldk * 8 + 64 + 128;
-    };
     const bool force_scalar = force && strcmp(force, "scalar") == 0;
     std::vector<Item2D> items2;
-    std::vector<ItemG> itemsG;
+    std::vector<ItemD2> itemsG;
     const bool force_nogemm = force && strcmp(force, "nogemm") == 0;
     int gemm_min_dk = MV2_NCMAX;              // bra blocks with more columns go to the DMMA kernel
     if (const char* e = getenv("RMB_GEMM_MIN_DK")) gemm_min_dk = atoi(e);
@@ -366,51 +362,59 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             flops += (kc ? 8.0 : 4.0) * dm1 * (double)dk1 * pr.dk2 + 8.0 * (double)pr.nd * dm1 * pr.dk2;
             opbytes += (kc ? 16.0 : 8.0) * dk1 * pr.dk2;
         }
-        // ---- DMMA kernel for wide real K blocks: all columns (<= 64 per item) in registers, Z staged once
+        // ---- DMMA kernel for wide real K blocks (rmb_matvec_dmma.cuh): 12 MMA warps = nst states x mt m-tiles of 8
+        //      rows, all columns (<= 64 per item) in registers, A fragments formed in registers from the staged ket rows
         if (!force_scalar && !force_nogemm && !kc && dk1 > gemm_min_dk && ndmax <= MV2_NDMAX) {
-            // rows per tile: nst * nrows <= MG_M, ket rows of all states of the tile must fit the buffer
-            int best_nt = 0, best_nst = 0;
+            const int nc_max = std::min(dk1, 8 * MD_NTMAX);
+            int ldk_max = ((nc_max + 7) / 8) * 8 + 4;
+            if (ldk_max % 16 != 4) ldk_max += 8;
+            int kt_max = 2;
+            for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p)
+                kt_max = std::max(kt_max, ((op->h_prods[p].dk2 + 3) & ~3) * ldk_max);
+            const int nprod_b = bra_begin[b + 1] - bra_begin[b];
+            int best_mt = 0, best_nst = 0;
             double best_util = -1;
-            const int nt0 = (dm1 + MG_M - 1) / MG_M;
-            for (int nt = nt0; nt <= nt0 + 3 && nt <= dm1; ++nt) {
-                const int nr = (dm1 + nt - 1) / nt;
-                int nst = std::max(1, MG_M / nr);
+            static const int mts[] = {12, 6, 4, 3, 2, 1};          // larger row tiles first: fewer halo rows
+            for (int mt : mts) {
+                const int nr = 8 * mt;
+                if (nr - 7 > dm1 && mt > 1) continue;              // a tile taller than the block: use a smaller mt
+                int nst = MD_MMA_WARPS / mt;
                 auto need = [&](int nst_) {
-                    size_t xb = 256;
+                    size_t xb = 16;
                     for (int p = bra_begin[b]; p < bra_begin[b + 1]; ++p) {
                         const ProdD& q = op->h_prods[p];
                         xb = std::max(xb, (size_t)nst_ * std::min(q.dm2, nr + h_span[p]) * (q.dk2 | 1));
                     }
-                    const int ncm = std::min(dk1, 8 * MG_NTMAX);
-                    const int ldk = ((ncm + 7) / 8) * 8 + 4 + ((((ncm + 7) / 8) * 8 + 4) % 16 == 4 ? 0 : 8);
-                    return itemG_smem((xb + 1) & ~(size_t)1, nr, ldk);
+                    return md_smem_bytes((int)xb, mt, kt_max, nprod_b);
                 };
-                while (nst > 1 && need(nst) > smem_budget) --nst;
-                if (need(nst) > smem_budget) continue;
-                const double util = (double)nr * nst / MG_M * ((double)dm1 / (nr * nt));
-                if (util > best_util + 1e-9) { best_util = util; best_nt = nt; best_nst = nst; }
+                while (nst > 1 && need(nst) > MD_SMEM_MAX) --nst;
+                if (need(nst) > MD_SMEM_MAX) continue;
+                const int ntile = (dm1 + nr - 1) / nr;
+                const double util = (double)dm1 / ((double)nr * ntile) * ((double)nst * mt / MD_MMA_WARPS);
+                if (util > best_util + 1e-9) { best_util = util; best_mt = mt; best_nst = nst; }
             }
-            if (best_nt > 0) {
-                const int nr_t = (dm1 + best_nt - 1) / best_nt;
-                for (int c0 = 0; c0 < dk1; c0 += 8 * MG_NTMAX)
+            if (best_mt > 0) {
+                const int nr_t = 8 * best_mt;
+                for (int c0 = 0; c0 < dk1; c0 += 8 * MD_NTMAX)
                     for (int r0 = 0; r0 < dm1; r0 += nr_t) {
-                        ItemG it;
+                        ItemD2 it;
                         it.bra_off = poff[b];
                         it.dk1 = dk1;
                         it.dm1 = dm1;
                         it.r0 = r0;
                         it.nrows = std::min(nr_t, dm1 - r0);
                         it.c0 = c0;
-                        it.nc = std::min(8 * MG_NTMAX, dk1 - c0);
+                        it.nc = std::min(8 * MD_NTMAX, dk1 - c0);
                         it.nt = (it.nc + 7) / 8;
                         it.ldk = it.nt * 8 + 4;
                         if (it.ldk % 16 != 4) it.ldk += 8;            // == 4 (mod 16): conflict-free B fragments
                         it.p_begin = bra_begin[b];
                         it.p_end = bra_begin[b + 1];
                         it.nst = best_nst;
+                        it.mt = best_mt;
                         it.desc_off = (int)gdesc.size();
                         it.pad = 0;
-                        int xbe = 256;
+                        int xbe = 16, ktd = 2;
                         for (int p = it.p_begin; p < it.p_end; ++p) {
                             const ProdD& q = op->h_prods[p];
                             int lo = q.dm2, hi = -1;
@@ -431,10 +435,12 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             ds.mreal = ds.pad2 = 0;
                             gdesc.push_back(ds);
                             xbe = std::max(xbe, it.nst * ds.nr * (q.dk2 | 1));
+                            ktd = std::max(ktd, ((q.dk2 + 3) & ~3) * it.ldk);
                         }
-                        it.xbuf_elems = (xbe + 1) & ~1;
-                        // K^T images [dk2 padded to MG_KCH][ldk] per product, zero padded, shared by the row
-                        // tiles of this (bra block, column tile)
+                        it.x_elems = xbe;
+                        it.kt_doubles = (ktd + 1) & ~1;
+                        // K^T images [dk2 padded to 4][ldk] per product, zero padded, shared by the row tiles of this
+                        // (bra block, column tile)
                         auto key = std::make_pair(-1 - b, c0);
                         auto found = kt_index.find(key);
                         if (found == kt_index.end()) {
@@ -443,7 +449,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                             kt_index[key] = off;
                             for (int p = it.p_begin; p < it.p_end; ++p) {
                                 const ProdD& q = op->h_prods[p];
-                                const int k2p = ((q.dk2 + MG_KCH - 1) / MG_KCH) * MG_KCH;
+                                const int k2p = (q.dk2 + 3) & ~3;
                                 for (int k2 = 0; k2 < k2p; ++k2)
                                     for (int c = 0; c < it.ldk; ++c)
                                         ktpool.push_back((k2 < q.dk2 && c < it.nc)
@@ -454,7 +460,8 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         } else {
                             it.kt_off = found->second;
                         }
-                        op->matvecG_smem = std::max(op->matvecG_smem, itemG_smem((size_t)it.xbuf_elems, it.nrows, it.ldk));
+                        op->matvecG_smem = std::max(op->matvecG_smem,
+                                                    md_smem_bytes(it.x_elems, it.mt, it.kt_doubles, it.p_end - it.p_begin));
                         itemsG.push_back(it);
                     }
                 continue;
@@ -614,12 +621,12 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
         items2.swap(sorted);
     }
     {
-        auto costG = [&](const ItemG& it) {
+        auto costG = [&](const ItemD2& it) {
             double c = 0;
-            for (int p = it.p_begin; p < it.p_end; ++p) c += (double)it.nrows * it.nst * op->h_prods[p].dk2 * it.nc;
+            for (int p = it.p_begin; p < it.p_end; ++p) c += (double)it.mt * it.nst * op->h_prods[p].dk2 * it.nc;
             return c;
         };
-        std::stable_sort(itemsG.begin(), itemsG.end(), [&](const ItemG& a, const ItemG& b) { return costG(a) > costG(b); });
+        std::stable_sort(itemsG.begin(), itemsG.end(), [&](const ItemD2& a, const ItemD2& b) { return costG(a) > costG(b); });
     }
     op->nitemsG = (int)itemsG.size();
     for (auto& it : itemsG) op->h_itemG_states.push_back(it.nst);
@@ -763,11 +770,11 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             }
         }
     }
-    if ((rc = upload((ItemG**)&op->d_itemsG, itemsG.data(), itemsG.size()))) return rc;
+    if ((rc = upload((ItemD2**)&op->d_itemsG, itemsG.data(), itemsG.size()))) return rc;
     {
         static size_t g_gemm_smem = 16 * 1024;
         if (op->matvecG_smem > g_gemm_smem) {
-            RMB_CUDA(cudaFuncSetAttribute(k_matvec_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->matvecG_smem));
+            RMB_CUDA(cudaFuncSetAttribute(k_matvec_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->matvecG_smem));
             g_gemm_smem = op->matvecG_smem;
         }
     }
@@ -979,6 +986,12 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         op->n_matvec_launches++;
         return RMB_OK;
     }
+    if (op->nnz_dirty && op->ngdesc > 0) {
+        // surviving diagonals per (item, product) descriptor of the tiled and DMMA kernels, after a field update
+        k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask, op->d_tab_cplx);
+        op->nnz_dirty = false;
+        op->n_launches++;
+    }
     if (op->nitems2 > 0) {
         // work units (item, first state) for this batch size; rebuilt only when the size changes
         if (op->units_nstates != nstates) {
@@ -1014,11 +1027,6 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             op->nunits = hit->second.second;
             op->units_nstates = nstates;
         }
-        if (op->nnz_dirty) {
-            k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask, op->d_tab_cplx);
-            op->nnz_dirty = false;
-            op->n_launches++;
-        }
         if (op->k_complex)
             k_matvec_tiled<true><<<op->nunits, MV2_THREADS, op->matvec2_smem, st>>>(
                 (const Unit2D*)op->d_units, (const Item2D*)op->d_items2, (const ProdS*)op->d_gdesc,
@@ -1035,9 +1043,18 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         if (op->unitsG_nstates != nstates) {
             auto hit = op->unitsG_cache.find(nstates);
             if (hit == op->unitsG_cache.end()) {
+                // a CTA walks `tl` consecutive state tiles of one item (one CTA per SM: descriptors, barriers and the
+                // producer pipeline are set up once); fewer, longer CTAs while the grid still fills the SMs ~6 times
                 std::vector<Unit2D> units;
-                for (int i = 0; i < op->nitemsG; ++i)
-                    for (long long s0 = 0; s0 < nstates; s0 += op->h_itemG_states[i]) units.push_back({i, (int)s0, 1, 0});
+                long long ntile_total = 0;
+                for (int i = 0; i < op->nitemsG; ++i) ntile_total += (nstates + op->h_itemG_states[i] - 1) / op->h_itemG_states[i];
+                int tl = (int)std::max<long long>(1, std::min<long long>(MV2_TILES_MAX, ntile_total / (6 * op->num_sms)));
+                if (const char* e = getenv("RMB_DMMA_TILES")) tl = std::max(1, std::min(MV2_TILES_MAX, atoi(e)));
+                for (int i = 0; i < op->nitemsG; ++i) {
+                    const long long nst = op->h_itemG_states[i];
+                    for (long long s0 = 0; s0 < nstates; s0 += nst * tl)
+                        units.push_back({i, (int)s0, (int)std::min<long long>(tl, (nstates - s0 + nst - 1) / nst), 0});
+                }
                 if (op->unitsG_cache.size() >= 16) {
                     RMB_CUDA(cudaStreamSynchronize(st));
                     for (auto& kv : op->unitsG_cache) cudaFree(kv.second.first);
@@ -1053,9 +1070,9 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             op->nunitsG = hit->second.second;
             op->unitsG_nstates = nstates;
         }
-        k_matvec_gemm<<<op->nunitsG, MG_THREADS, op->matvecG_smem, st>>>(
-            (const Unit2D*)op->d_unitsG, (const ItemG*)op->d_itemsG, (const ProdS*)op->d_gdesc,
-            (const MfEntry*)op->d_ent_cent, op->d_tab_mask, op->d_ktpool, X, Y, ldx, ldy, (int)nstates, active,
+        k_matvec_dmma<<<op->nunitsG, MD_THREADS, op->matvecG_smem, st>>>(
+            (const Unit2D*)op->d_unitsG, (const ItemD2*)op->d_itemsG, (const ProdS*)op->d_gdesc,
+            (const MfEntry*)op->d_ent_cent, op->d_ktpool, X, Y, ldx, ldy, (int)nstates, active,
             ep.scale, ep.scale_stride, ep.pdot, ep.npart, op->nitems2);
         op->n_launches++;
     }

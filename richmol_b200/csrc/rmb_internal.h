@@ -104,9 +104,9 @@ struct rmb_operator {
     long long units_nstates = -1;
     int nunits = 0;
     std::vector<int> h_item2_states; // states per CTA of each tiled item
-    // DMMA matvec for wide K blocks (rmb_matvec_gemm.cuh)
+    // DMMA matvec for wide K blocks (rmb_matvec_dmma.cuh)
     int nitemsG = 0;
-    void* d_itemsG = nullptr;        // ItemG[]
+    void* d_itemsG = nullptr;        // ItemD2[]
     void* d_unitsG = nullptr;
     int nunitsG = 0;
     long long unitsG_nstates = -1;

@@ -468,19 +468,34 @@ class CarTens:
         return self.full_form(mat, repres, thresh)
 
     def full_form(self, mat, repres='csr_matrix', thresh=None):
-        """Block representation -> 2D matrix (richmol/field.py:659-692)."""
-        rows = []
+        """Block representation -> 2D matrix (richmol/field.py:659-692).  Assembled from the COO triplets of the
+        blocks that exist (the reference builds a dense zero matrix for every missing block pair, which at
+        N ~ 10^6 is the most expensive thing it ever does)."""
+        roff, coff, ind = {}, {}, 0
         for J1 in self.Jlist1:
             for sym1 in self.symlist1[J1]:
-                row = []
-                for J2 in self.Jlist2:
-                    for sym2 in self.symlist2[J2]:
-                        m = mat.get((J1, J2), {}).get((sym1, sym2))
-                        if m is None:
-                            m = sp.csr_matrix((self.dim1[J1][sym1], self.dim2[J2][sym2]))
-                        row.append(m)
-                rows.append(row)
-        res = sp.bmat(rows)
+                roff[(J1, sym1)] = ind
+                ind += self.dim1[J1][sym1]
+        nrow, ind = ind, 0
+        for J2 in self.Jlist2:
+            for sym2 in self.symlist2[J2]:
+                coff[(J2, sym2)] = ind
+                ind += self.dim2[J2][sym2]
+        ncol = ind
+        rows, cols, vals = [], [], []
+        for (J1, J2), mat_J in mat.items():
+            for (sym1, sym2), m in mat_J.items():
+                if (J1, sym1) not in roff or (J2, sym2) not in coff:
+                    continue
+                m = sp.coo_matrix(m)
+                rows.append(m.row.astype(np.int64) + roff[(J1, sym1)])
+                cols.append(m.col.astype(np.int64) + coff[(J2, sym2)])
+                vals.append(m.data)
+        if vals:
+            res = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                                shape=(nrow, ncol))
+        else:
+            res = sp.coo_matrix((nrow, ncol))
         return res.toarray() if repres == 'dense' else getattr(sp, repres)(res)
 
 

@@ -4,7 +4,7 @@
   * BASELINE config 2 at full size: the bench's operator, its 500-state batch and tiles, >= 10 bench field steps,
     32 sampled rows against `port.update_step` at 1e-10 with identical Lanczos orders;
   * the OCS Jmax = 60 bench operator with a 512-state batch through `k_matvec_lin`;
-  * one full-band H2S step at Jmax >= 40 with 32 states through `k_matvec_gemm`;
+  * one full-band H2S step at Jmax >= 40 with 32 states through `k_matvec_dmma`;
   * the bench's own self-check helper on a small workload.
 
 Every comparison follows richmol/tdse.py:417-486 (`_expmv_lanczos`) on every sampled row via the pinned port.
@@ -123,7 +123,7 @@ def test_ocs_jmax60_lin_kernel_512_states_against_oracle():
 
 def test_h2s_full_band_dmma_step_32_states():
     """H2S Jmax = 40, all J (N = 91 881, dim_k up to 21): one optical-centrifuge step (complex MF, Delta m = 0, +-2)
-    with 32 states; bra blocks with dim_k > 12 run through k_matvec_gemm, the rest through k_matvec_tiled."""
+    with 32 states; bra blocks with dim_k > 12 run through k_matvec_dmma, the rest through k_matvec_tiled."""
     import ctypes as C
     import torch
     from richmol_b200 import _lib
