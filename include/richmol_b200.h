@@ -127,7 +127,9 @@ int32_t rmb_propagate_step_host(rmb_operator* op, const double* psi_in_host, dou
 /* Same as rmb_propagate_step_host, and additionally evaluates <psi_s|O_o|psi_s> of the PROPAGATED states for
  * `nobs` operators on the device before the download (expval_host: [nobs][nstates] complex) -- what the
  * reference's examples do on the host after every update (examples/ocs_alignment.py:96-100), without a
- * second upload.  The ensemble is processed in chunks so that uploads, kernels and downloads overlap.     */
+ * second upload.  The ensemble is processed in chunks so that uploads, kernels and downloads overlap.
+ * `h0phase_host` may also be a DEVICE pointer (detected with cudaPointerGetAttributes): callers that keep the
+ * phase vector resident avoid a pageable 16 N byte upload per call.                                        */
 int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host, double* psi_out_host,
                                     int64_t nstates, int64_t ld, double fac_re, double fac_im,
                                     double tol, int32_t maxorder, const double* h0phase_host,

@@ -9,6 +9,7 @@
 #include <numeric>
 
 #include "rmb_kernels.cuh"
+#include "rmb_lanczos.cuh"
 #include "rmb_matvec.cuh"
 #include "rmb_fused.cuh"
 #include "rmb_matvec_dmma.cuh"
@@ -104,6 +105,9 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_pdot);
     cudaFree(op->d_pnrm);
     cudaFree(op->d_pconv);
+    cudaFree(op->d_pg0);
+    cudaFree(op->d_gdiag);
+    cudaFree(op->d_ticket);
     cudaFree(op->d_ctrl);
     if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
     cudaFree(op->d_stage);
@@ -1139,6 +1143,10 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     if ((rc = ensure(&op->d_pdot, (size_t)cap * np))) return rc;
     if ((rc = ensure(&op->d_pnrm, (size_t)cap * op->nchunk))) return rc;
     if ((rc = ensure(&op->d_pconv, (size_t)cap * op->nchunk))) return rc;
+    if ((rc = ensure(&op->d_pg0, (size_t)cap * op->nchunk))) return rc;
+    if ((rc = ensure(&op->d_gdiag, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->d_ticket, (size_t)cap))) return rc;
+    RMB_CUDA(cudaMemset(op->d_ticket, 0, std::max<size_t>(1, (size_t)cap) * sizeof(unsigned)));
     if ((rc = ensure(&op->d_ctrl, (size_t)4 * (maxorder + 2)))) return rc;
     if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
     RMB_CUDA(cudaMallocHost((void**)&op->h_ctrl, sizeof(int) * 4 * (maxorder + 2)));
@@ -1194,12 +1202,24 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     const bool lin = op->lin_ok && B >= 4 * op->lin_T;      // large batches of linear rotors: sliding window
     const bool fused = lin || fused_dot(op);
     const int npart = lin ? op->lin_npart : dot_parts(op);
+    // sliced grids of the vector kernels: a CTA walks `cps` consecutive chunks of one state (~12 CTAs per SM in total)
+    auto slices = [&](int nchunk_, int* nsl_, int* cps_) {
+        const long long want = std::max<long long>(1, (12LL * op->num_sms + B - 1) / B);
+        const int nsl0 = (int)std::min<long long>(nchunk_, want);
+        *cps_ = (nchunk_ + nsl0 - 1) / nsl0;
+        *nsl_ = (nchunk_ + *cps_ - 1) / *cps_;
+    };
+    int nsl_p, cps_p, nsl_u, cps_u;
+    slices(nch, &nsl_p, &cps_p);
+    slices(nchunks(n), &nsl_u, &cps_u);
+    static const bool gram = !(getenv("RMB_GRAM") && atoi(getenv("RMB_GRAM")) == 0);
     int rc;
     if ((rc = ensure_slab(op, 2, st))) return rc;
     RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
     k_init_states<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, op->d_order, op->d_rinv,
                                                                op->d_beta, bs, (int)B);
-    k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], np, n, op->d_pmap);
+    k_phase_init_s<<<dim3((unsigned)nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], np, n, op->d_pmap,
+                                                                                cps_u, nchunks(n));
     op->n_launches += 2;
     int k = 0;
     std::vector<long long> act_hist;
@@ -1222,15 +1242,27 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, np, np, op->d_pdot, npart, op->d_active);
             op->n_launches += 2;
         }
-        k_small_a<<<(unsigned)B, 32, 0, st>>>(op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, ts, bs, k,
-                                              fac, op->d_ccur, op->d_ceff, op->d_dc, op->d_active);
-        k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, np, np, op->d_alpha, op->d_beta,
-                                                    op->d_rinv, op->d_dc, ts, bs, k, op->d_pnrm, op->d_pconv,
-                                                    nch, op->d_active);
-        k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_pnrm, op->d_pconv, nch, op->d_beta, op->d_rinv, bs, k,
-                                                       tol, maxorder, op->d_active, op->d_order, op->d_ctrl,
-                                                       op->d_slab_ptrs, np, n, op->d_pmap);
-        op->n_launches += 3;
+        if (gram && k < RMB_GRAM_KMAX) {
+            // one launch: recurrence + (last CTA per state) alpha/beta, small exponential, Gram-diagonal
+            // convergence metric, stop rule, zero-beta fallback
+            k_recur_gram<<<dim3((unsigned)nsl_p, (unsigned)B), VEC_THREADS, 0, st>>>(
+                op->d_w, op->d_slab_ptrs, np, np, op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, op->d_gdiag,
+                ts, bs, k, fac, op->d_ccur, op->d_ceff, op->d_pnrm, op->d_pg0, nsl_p, cps_p, nch, op->d_ticket, tol,
+                maxorder, op->d_active, op->d_order, op->d_ctrl, op->d_pmap, n);
+            op->n_launches += 1;
+        } else {
+            // explicit evaluation of sum |u_k - u_{k-1}|^2 over the Krylov history (many vectors: the Gram matrix is no
+            // longer close to diagonal once the three-term recurrence loses orthogonality)
+            k_small_a<<<(unsigned)B, 32, 0, st>>>(op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, ts, bs, k,
+                                                  fac, op->d_ccur, op->d_ceff, op->d_dc, op->d_active);
+            k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, np, np, op->d_alpha, op->d_beta,
+                                                        op->d_rinv, op->d_dc, ts, bs, k, op->d_pnrm, op->d_pconv,
+                                                        nch, op->d_active);
+            k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_pnrm, op->d_pconv, nch, op->d_beta, op->d_rinv, bs, k,
+                                                           tol, maxorder, op->d_active, op->d_order, op->d_ctrl,
+                                                           op->d_slab_ptrs, np, n, op->d_pmap);
+            op->n_launches += 3;
+        }
         op->n_iterations++;
         RMB_CUDA(cudaMemcpyAsync(op->h_ctrl + 4 * k, op->d_ctrl + 4 * k, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         RMB_CUDA(cudaEventRecord(op->it_events[k], st));
@@ -1246,8 +1278,8 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             break;
         }
     }
-    k_combine<<<ugrid, VEC_THREADS, 0, st>>>(op->d_slab_ptrs, np, n, op->d_ceff, ts, op->d_order, ph, psi, ld,
-                                             op->d_pmap);
+    k_combine_s<<<dim3((unsigned)nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(op->d_slab_ptrs, np, n, op->d_ceff, ts, op->d_order,
+                                                                             ph, psi, ld, op->d_pmap, cps_u, nchunks(n));
     op->n_launches++;
     RMB_CUDA(cudaGetLastError());
     // state-matvecs actually performed: all states in iteration 0, the survivors of k-1 in iteration k
@@ -1513,12 +1545,22 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
     }
     const cplx* ph = nullptr;
     if (h0phase_host) {
-        if (op->n > op->phase_elems) {
-            if ((rc = ensure(&op->d_phase, (size_t)op->n))) return rc;
-            op->phase_elems = op->n;
+        // the phase vector may already live on the device (the Python layer caches it there: uploading 16 N bytes of
+        // pageable memory on every call is a synchronous copy of milliseconds at N ~ 10^6)
+        cudaPointerAttributes pa;
+        const bool on_device = cudaPointerGetAttributes(&pa, h0phase_host) == cudaSuccess &&
+                               (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (on_device) {
+            ph = (const cplx*)h0phase_host;
+        } else {
+            if (op->n > op->phase_elems) {
+                if ((rc = ensure(&op->d_phase, (size_t)op->n))) return rc;
+                op->phase_elems = op->n;
+            }
+            RMB_CUDA(cudaMemcpyAsync(op->d_phase, h0phase_host, sizeof(cplx) * op->n, cudaMemcpyHostToDevice, st));
+            ph = op->d_phase;
         }
-        RMB_CUDA(cudaMemcpyAsync(op->d_phase, h0phase_host, sizeof(cplx) * op->n, cudaMemcpyHostToDevice, st));
-        ph = op->d_phase;
     }
     // Chunked pipeline: upload of chunk c+1 and download of chunk c-1 overlap the propagation of chunk c
     // (PCIe is full duplex; uploads on s_in, downloads on s_out, kernels on the caller's stream).

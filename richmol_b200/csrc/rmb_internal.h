@@ -173,6 +173,9 @@ struct rmb_operator {
     rmb::cplx* d_pdot = nullptr;     // [S][nchunk]
     double* d_pnrm = nullptr;        // [S][nchunk]
     double* d_pconv = nullptr;       // [S][nchunk]
+    double* d_pg0 = nullptr;         // [S][nchunk]  partial <V_0,V_0> (k_recur_gram, k = 0)
+    double* d_gdiag = nullptr;       // [S][maxorder+1]  <V_i,V_i> (diagonal of the Gram matrix of the Krylov vectors)
+    unsigned* d_ticket = nullptr;    // [S]  arrival counter of k_recur_gram's CTAs per state
     int* d_ctrl = nullptr;           // per iteration k: [4k] states still active, [4k+1] maxorder flag
     int* h_ctrl = nullptr;           // pinned mirror
     int nchunk = 0;

@@ -114,10 +114,15 @@ class TDSE():
         return t_c
 
     # ------------------------------------------------------------------------------------------
-    def init_state(self, H, temp=None, thresh=1e-3, zpe=None, sparse=False):
+    def init_state(self, H, temp=None, thresh=1e-3, zpe=None, sparse=False, device_eigh=False):
         """Initial state vectors: eigenfunctions of `H`, Boltzmann-weighted for temp > 0
         (richmol/tdse.py:177-262).  Rows are sqrt(w_i)-scaled; the kept prefix is cut in basis
-        order by cumulative weight.  Host-side, once per run."""
+        order by cumulative weight.  Host-side, once per run.
+
+        `device_eigh=True` (extension): the dense diagonalisation of a field-dressed `H`
+        (richmol/tdse.py:231-233, `np.linalg.eigh` of the full matrix) runs on the GPU.  Eigenvalues agree to
+        rounding; eigenvectors are only defined up to a phase (and a rotation inside degenerate subspaces), so
+        the rows span the same eigenspaces but are not bit-identical to the host path."""
         if temp is not None:
             assert (temp >= 0), f"temperature `temp` has negative value: '{temp}'"
         assert (thresh >= 0), f"partition function threshold `thresh` has negative or zero value: '{thresh}'"
@@ -141,7 +146,13 @@ class TDSE():
             vecs = diags(np.ones(len(enrs)), format='csr')
         else:
             hmat = H.tomat(form="full", repres="dense")
-            enrs, vecs = np.linalg.eigh(hmat)
+            if device_eigh:
+                import torch
+                _lib.require_device()
+                e_d, v_d = torch.linalg.eigh(torch.from_numpy(np.ascontiguousarray(hmat)).cuda())
+                enrs, vecs = e_d.cpu().numpy(), v_d.cpu().numpy()
+            else:
+                enrs, vecs = np.linalg.eigh(hmat)
             vecs = csr_matrix(vecs)
         enrs = np.array(enrs.real if np.iscomplexobj(enrs) else enrs, dtype=np.float64)
 
@@ -327,7 +338,10 @@ class TDSE():
               or not vout.flags.c_contiguous):
             raise ValueError("`out` must be a C-contiguous complex128 array of the shape of `vecs`")
         orders = np.zeros(nst, dtype=np.int32)
-        ph = np.ascontiguousarray(phase, dtype=np.complex128) if phase is not None else None
+        ph_dev = None
+        if phase is not None:
+            import torch
+            ph_dev = self._h0_phase_device(torch.device("cuda", torch.cuda.current_device()))   # cached on the device
         # extension: observables of the propagated states evaluated on the device before the download
         obs = [_as_cartens(O, {}) for O in kwargs.get('expect', ())]
         for O in obs:
@@ -338,7 +352,7 @@ class TDSE():
         expv = np.zeros((len(obs), nst), dtype=np.complex128)
         status = lib.rmb_propagate_step_host_obs(
             op.handle, vin.ctypes.data, vout.ctypes.data, nst, N, exp_fac.real, exp_fac.imag,
-            float(tol), 100, ph.ctypes.data if ph is not None else None, int(skip),
+            float(tol), 100, ph_dev.data_ptr() if ph_dev is not None else None, int(skip),
             orders.ctypes.data, len(obs), handles, expv.ctypes.data, stream)
         self._orders = orders
         self.last_expect = expv

@@ -225,3 +225,22 @@ def test_external_propagator_is_refused():
         tdse.update(H, v, H0=m["h0"], propag="external")
     with pytest.raises(AssertionError):
         tdse.update(H, v, H0=m["h0"], propag="other")
+
+
+def test_dressed_init_state_with_device_eigensolver():
+    """`init_state(h0 + Hdc, temp, device_eigh=True)` -- same energies / Boltzmann weights as the host
+    path (richmol/tdse.py:231-257) and every row an eigenvector of the dressed Hamiltonian."""
+    m = synth.ocs(12)
+    Hdc = -1 * m["dip"] * AUDIP
+    Hdc.field([1.2e6, 0.0, 1.7e6])
+    H = m["h0"] + Hdc
+    tdse = TDSE(t_end=1, dt=0.01)
+    tdse.time_grid()
+    a = tdse.init_state(H, temp=1.0)
+    b = tdse.init_state(H, temp=1.0, device_eigh=True)
+    assert a.shape == b.shape
+    assert np.allclose(np.linalg.norm(a, axis=1), np.linalg.norm(b, axis=1), rtol=1e-10, atol=1e-14)
+    Hm = H.tomat(form="full", repres="dense")
+    for row in b:
+        u = row / np.linalg.norm(row)
+        assert np.linalg.norm(Hm @ u - np.vdot(u, Hm @ u) * u) < 1e-9 * np.abs(Hm).max()
