@@ -176,6 +176,13 @@ int32_t rmb_matvec_timing(rmb_operator* op, int32_t enable, double* ms_out, int6
  * (k_matvec_dmma), scalar items (k_matvec_scalar), sliding-window kernel usable (k_matvec_lin),
  * single-launch step usable (k_lanczos_fused), max dim_k, padded dimension, products }            */
 int32_t rmb_operator_info(const rmb_operator* op, int64_t* out8);
+/* SURVEY 8f-3 -- generator of the laboratory-frame tensor factors (richmol/rot/labtens.py:482-523, which loops over
+ * py3nj calls in Python): out[c][a][b] = pref * (-1)^|qa| * sum_sigma coef[c][sigma+omega] * 3j(j2 omega j1; qb sigma -qa),
+ * qa = a - j1, qb = b - j2; complex [ncoef][2 j1 + 1][2 j2 + 1], host buffers.  coef = Ux[cart,(omega,sigma)],
+ * pref = sqrt((2 j1 + 1)(2 j2 + 1)) gives the M tensor of every Cartesian component; coef = (Us T)_{omega,sigma},
+ * pref = 1 the primitive K tensor over |J,k>.                                                               */
+int32_t rmb_threej_band(int32_t j1, int32_t j2, int32_t omega, int32_t ncoef, const double* coef_host, double pref,
+                        double* out_host, void* stream);
 /* FP64 roofline denominators measured on the current device (MEASURED_PEAKS.json has no FP64 entry):
  * register-resident DFMA and DMMA (mma.sync.m8n8k4.f64) loops over all SMs, best of 3, TFLOP/s.    */
 int32_t rmb_fp64_peak(double* dfma_tflops, double* dmma_tflops, void* stream);

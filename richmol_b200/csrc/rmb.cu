@@ -1223,6 +1223,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     op->n_launches += 2;
     int k = 0;
     std::vector<long long> act_hist;
+    static const int LOOK = getenv("RMB_LOOKAHEAD") ? std::max(1, std::min(4, atoi(getenv("RMB_LOOKAHEAD")))) : 2;
     for (;; ++k) {
         if ((rc = ensure_slab(op, k + 1, st))) return rc;
         cplx* Vk = op->slabs[k];
@@ -1266,15 +1267,21 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
         op->n_iterations++;
         RMB_CUDA(cudaMemcpyAsync(op->h_ctrl + 4 * k, op->d_ctrl + 4 * k, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         RMB_CUDA(cudaEventRecord(op->it_events[k], st));
-        // inspect the previous iteration (its kernels have most likely finished by now)
-        if (k >= 1) {
-            RMB_CUDA(cudaEventSynchronize(op->it_events[k - 1]));
-            act_hist.push_back(op->h_ctrl[4 * (k - 1)]);
-            if (op->h_ctrl[4 * (k - 1) + 1]) *hit_maxorder = true;
-            if (op->h_ctrl[4 * (k - 1)] == 0) break;
+        // inspect iteration k - LOOK (its kernels have most likely finished by now): the host stays LOOK iterations
+        // ahead of the GPU, so its wake-up and launch latencies never leave the GPU idle; the price is LOOK enqueued
+        // iterations in which every state is inactive (a few microseconds each)
+        if (k >= LOOK) {
+            RMB_CUDA(cudaEventSynchronize(op->it_events[k - LOOK]));
+            act_hist.push_back(op->h_ctrl[4 * (k - LOOK)]);
+            if (op->h_ctrl[4 * (k - LOOK) + 1]) *hit_maxorder = true;
+            if (op->h_ctrl[4 * (k - LOOK)] == 0) break;
         }
-        if (k + 1 >= maxorder + 1) {   // safety net: cannot happen (k_small_b retires every state)
+        if (k + 1 >= maxorder + 1) {   // every state has been retired by iteration maxorder - 1: read what is outstanding
             RMB_CUDA(cudaEventSynchronize(op->it_events[k]));
+            for (int j = std::max(0, k - LOOK + 1); j <= k; ++j) {
+                act_hist.push_back(op->h_ctrl[4 * j]);
+                if (op->h_ctrl[4 * j + 1]) *hit_maxorder = true;
+            }
             break;
         }
     }
@@ -1564,9 +1571,13 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
     }
     // Chunked pipeline: upload of chunk c+1 and download of chunk c-1 overlap the propagation of chunk c
     // (PCIe is full duplex; uploads on s_in, downloads on s_out, kernels on the caller's stream).
-    int want = 3;
+    // chunk count: by bytes (a chunk of >= 48 MB keeps the copy engines efficient; 3-6 chunks hide all but the first
+    // upload and the last download), never below 2 states per chunk
+    const double mbytes = (double)elems * 16.0 / 1e6;
+    int want = (int)std::max(1.0, std::min(6.0, mbytes / 48.0));
+    if (nstates >= 128) want = std::max(want, 3);
     if (const char* e = getenv("RMB_HOST_CHUNKS")) want = std::max(1, atoi(e));
-    long long cs = nstates >= 128 ? (nstates + want - 1) / want : nstates;
+    long long cs = (nstates + want - 1) / want;
     cs = std::max<long long>(2, (cs + 1) & ~1LL);
     const int nchunk = (int)((nstates + cs - 1) / cs);
     while ((int)op->pipe_events.size() < 2 * nchunk + 1) {
@@ -1574,6 +1585,17 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
         RMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         op->pipe_events.push_back(e);
     }
+    // RMB_E2E_TRACE=1: device timeline of the pipeline on stderr (upload / compute / download end of every chunk)
+    static const bool trace = getenv("RMB_E2E_TRACE") && atoi(getenv("RMB_E2E_TRACE")) != 0;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s_) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s_);
+        tev.push_back(e);
+    };
+    mark(st);
     // uploads must not overtake the previous call's downloads of the same staging buffer
     RMB_CUDA(cudaEventRecord(op->pipe_events[2 * nchunk], st));
     RMB_CUDA(cudaStreamWaitEvent(op->s_in, op->pipe_events[2 * nchunk], 0));
@@ -1582,6 +1604,7 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
         RMB_CUDA(cudaMemcpyAsync(op->d_stage + c0 * ld, (const cplx*)psi_in_host + c0 * ld, sizeof(cplx) * b * ld,
                                  cudaMemcpyHostToDevice, op->s_in));
         RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c], op->s_in));
+        mark(op->s_in);
     }
     int result = RMB_OK;
     for (int c = 0; c < nchunk; ++c) {
@@ -1597,15 +1620,29 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
             if (rc != RMB_OK) return rc;
         }
         RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c + 1], st));
+        mark(st);
         RMB_CUDA(cudaStreamWaitEvent(op->s_out, op->pipe_events[2 * c + 1], 0));
         RMB_CUDA(cudaMemcpyAsync((cplx*)psi_out_host + c0 * ld, op->d_stage + c0 * ld, sizeof(cplx) * b * ld,
                                  cudaMemcpyDeviceToHost, op->s_out));
+        mark(op->s_out);
     }
     if (nobs > 0)
         RMB_CUDA(cudaMemcpyAsync(expval_host, op->d_expv, sizeof(cplx) * (size_t)nobs * nstates,
                                  cudaMemcpyDeviceToHost, st));
     RMB_CUDA(cudaStreamSynchronize(st));
     RMB_CUDA(cudaStreamSynchronize(op->s_out));
+    if (trace && !tev.empty()) {
+        fprintf(stderr, "[rmb e2e] %d chunks of %lld states:", nchunk, cs);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            const int nc_ = nchunk;
+            const char* what = (int)i <= nc_ ? "up" : (((int)i - nc_) % 2 ? "comp" : "down");
+            fprintf(stderr, " %s %.2f", what, ms);
+        }
+        fprintf(stderr, " ms\n");
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     if (result == RMB_ERR_MAXORDER) {
         char buf[128];
         snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
@@ -1710,6 +1747,34 @@ int32_t rmb_operator_work(rmb_operator* op, double* flops_per_state, double* op_
     }
     if (flops_per_state) *flops_per_state = fl;
     if (op_bytes) *op_bytes = by;
+    return RMB_OK;
+}
+
+int32_t rmb_threej_band(int32_t j1, int32_t j2, int32_t omega, int32_t ncoef, const double* coef_host, double pref,
+                        double* out_host, void* stream) {
+    if (j1 < 0 || j2 < 0 || omega < 0 || ncoef <= 0 || !coef_host || !out_host) {
+        set_error("threej_band: bad arguments");
+        return RMB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nco = (size_t)ncoef * (2 * omega + 1);
+    const size_t nout = (size_t)ncoef * (2 * j1 + 1) * (2 * j2 + 1);
+    cplx *d_coef = nullptr, *d_out = nullptr;
+    RMB_CUDA(cudaMalloc((void**)&d_coef, nco * sizeof(cplx)));
+    if (cudaMalloc((void**)&d_out, nout * sizeof(cplx)) != cudaSuccess) {
+        cudaFree(d_coef);
+        return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    }
+    cudaMemcpyAsync(d_coef, coef_host, nco * sizeof(cplx), cudaMemcpyHostToDevice, st);
+    const int nt = 256;
+    const unsigned nb = (unsigned)std::min<size_t>((nout + nt - 1) / nt, 148 * 16);
+    k_threej_band<<<nb, nt, 0, st>>>(j1, j2, omega, ncoef, d_coef, pref, d_out);
+    cudaMemcpyAsync(out_host, d_out, nout * sizeof(cplx), cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_coef);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "threej_band");
+    RMB_CUDA(cudaGetLastError());
     return RMB_OK;
 }
 

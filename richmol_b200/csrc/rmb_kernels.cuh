@@ -690,4 +690,49 @@ __global__ void k_peak_dmma(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- laboratory-frame tensor generator (richmol/rot/labtens.py:482-523) -------------------------
+// Wigner 3j symbol (j1 j2 j3; m1 m2 m3) for integer arguments by the Racah sum with log-factorials; with the small
+// tensor rank j2 <= 2 used here the sum has at most 2 j2 + 1 terms and no cancellation to speak of.
+__device__ __forceinline__ double lfact(int n) { return lgamma((double)(n > 0 ? n : 0) + 1.0); }
+__device__ double wigner3j_int(int j1, int j2, int j3, int m1, int m2, int m3) {
+    if (m1 + m2 + m3 != 0 || abs(m1) > j1 || abs(m2) > j2 || abs(m3) > j3 || j3 < abs(j1 - j2) || j3 > j1 + j2) return 0.0;
+    const double lnpref = 0.5 * (lfact(j1 + j2 - j3) + lfact(j1 - j2 + j3) + lfact(-j1 + j2 + j3) - lfact(j1 + j2 + j3 + 1) +
+                                 lfact(j1 + m1) + lfact(j1 - m1) + lfact(j2 + m2) + lfact(j2 - m2) + lfact(j3 + m3) +
+                                 lfact(j3 - m3));
+    const int tmin = max(0, max(j2 - j3 - m1, j1 - j3 + m2));
+    const int tmax = min(j1 + j2 - j3, min(j1 - m1, j2 + m2));
+    double res = 0.0;
+    for (int t = tmin; t <= tmax; ++t) {
+        const double lnden = lfact(t) + lfact(j3 - j2 + t + m1) + lfact(j3 - j1 + t - m2) + lfact(j1 + j2 - j3 - t) +
+                             lfact(j1 - t - m1) + lfact(j2 - t + m2);
+        const double term = exp(lnpref - lnden);
+        res += (t & 1) ? -term : term;
+    }
+    return (abs(j1 - j2 - m3) & 1) ? -res : res;
+}
+
+// out[c][a][b] = pref * (-1)^|qa| * sum_sigma coef[c][sigma + omega] * 3j(j2 omega j1; qb sigma -qa),  qa = a - j1, qb = b - j2
+// (a, b: positions of the projection quantum numbers -j..j).  With coef = Ux[cart,(omega,sigma)] and
+// pref = sqrt((2 j1 + 1)(2 j2 + 1)) this is the M tensor (labtens.py:504-523); with coef = (Us T)_{omega sigma} and
+// pref = 1 the primitive K tensor over |J,k> (labtens.py:482-502).  Only b = a - j1 + j2 - sigma contributes.
+__global__ void k_threej_band(int j1, int j2, int omega, int ncoef, const cplx* __restrict__ coef, double pref,
+                              cplx* __restrict__ out) {
+    const int d1 = 2 * j1 + 1, d2 = 2 * j2 + 1;
+    const long long total = (long long)ncoef * d1 * d2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % d2);
+        const int a = (int)((i / d2) % d1);
+        const int c = (int)(i / ((long long)d1 * d2));
+        const int qa = a - j1, qb = b - j2;
+        const int sigma = qa - qb;
+        cplx v = make_double2(0.0, 0.0);
+        if (abs(sigma) <= omega) {
+            const double tj = wigner3j_int(j2, omega, j1, qb, sigma, -qa) * pref * ((abs(qa) & 1) ? -1.0 : 1.0);
+            const cplx cf = coef[c * (2 * omega + 1) + sigma + omega];
+            v = make_double2(cf.x * tj, cf.y * tj);
+        }
+        out[i] = v;
+    }
+}
+
 }  // namespace rmb
