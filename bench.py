@@ -859,20 +859,23 @@ def parity_check(w, m, tdse, rows, ctx, nsteps=2):
             "oracle": "oracle/port.py (pinned to the unmodified reference)", "seconds": round(time.perf_counter() - t0, 1)}
 
 
-def gpu_main(args):
+def gpu_main(args, cpu_also=None):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from richmol_b200.ensemble import bind_to_gpu_numa
+    cpus = bind_to_gpu_numa(local)                      # before any pinned allocation (first touch on the GPU's node)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = dict(world=world, rank=rank, local=local, dev=torch.device("cuda", local))
+    ctx = dict(world=world, rank=rank, local=local, dev=torch.device("cuda", local), cpu_also=cpu_also or {})
     head_w = WORKLOADS[args.workload]()
     if args.asym_states:
         Asym.nstates = args.asym_states
     head = gpu_workload(head_w, args, True, ctx)
+    cpu_also = ctx.get("cpu_also", {})
     others = []
     for name in args.also:
         if name == args.workload:
@@ -884,6 +887,8 @@ def gpu_main(args):
             if world > 1:
                 raise
         if r is not None:
+            if name in cpu_also:
+                r["cpu_baseline"] = cpu_also[name]
             others.append(r)
     if world > 1:
         dist.destroy_process_group()
@@ -897,6 +902,8 @@ def gpu_main(args):
         "roofline": head["roofline"], "parity": head["parity"],
         "workloads": [dict(r, n_gpus=world) for r in others],
     }
+    line["config"]["cpu_affinity"] = (f"rank 0 bound to {len(cpus)} cores of its GPU's NUMA node (NVML ideal affinity)"
+                                      if cpus else "not bound")
     line["config"]["baseline_config"] = head["baseline_config"]
     return line
 
@@ -943,16 +950,21 @@ def main():
         }))
         return
 
-    cpu = None
+    cpu, cpu_also = None, {}
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (workers are spawned, not forked)
-        m = build_model(w)
-        r = cpu_run(w, m, 2, 1, kind=args.cpu_kind)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-               "one_core": {"value": r["one_core"], "unit": UNIT, "cores": 1,
-                            "sample": "one process alone, 1 state x 1 step of the same workload"}}
-        del m
-    line = gpu_main(args)
+        def baseline(wl, steps):
+            m = build_model(wl)
+            r = cpu_run(wl, m, steps, 1, kind=args.cpu_kind)
+            return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                    "one_core": {"value": r["one_core"], "unit": UNIT, "cores": 1,
+                                 "sample": "one process alone, 1 state x 1 step of the same workload"}}
+        cpu = baseline(w, 2)
+        # the light secondary workloads get their own CPU figure (seconds each); the heavy ones (asym) do not
+        for name in args.also:
+            if name != args.workload and name in ("ocs_align", "h2o", "ocs_mixed", "ocs_batch"):
+                cpu_also[name] = baseline(WORKLOADS[name](), 3)
+    line = gpu_main(args, cpu_also)
     if line is not None:
         if cpu is not None:
             line["cpu_baseline"] = cpu

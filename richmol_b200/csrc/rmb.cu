@@ -111,6 +111,7 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_ctrl);
     if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
     cudaFree(op->d_stage);
+    cudaFree(op->d_pipe_orders);
     cudaFree(op->d_expv);
     if (op->s_in) cudaStreamDestroy(op->s_in);
     if (op->s_out) cudaStreamDestroy(op->s_out);
@@ -1148,8 +1149,12 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     if ((rc = ensure(&op->d_ticket, (size_t)cap))) return rc;
     RMB_CUDA(cudaMemset(op->d_ticket, 0, std::max<size_t>(1, (size_t)cap) * sizeof(unsigned)));
     if ((rc = ensure(&op->d_ctrl, (size_t)4 * (maxorder + 2)))) return rc;
+    // pinned AND mapped: the control words are published by a one-warp kernel (k_publish) instead of a D2H memcpy on the
+    // compute stream, which would queue behind any large download in flight on the same copy engine (the host-buffer
+    // pipeline's own downloads serialised every chunk's Lanczos loop that way)
     if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
-    RMB_CUDA(cudaMallocHost((void**)&op->h_ctrl, sizeof(int) * 4 * (maxorder + 2)));
+    RMB_CUDA(cudaHostAlloc((void**)&op->h_ctrl, sizeof(int) * 4 * (maxorder + 2), cudaHostAllocMapped));
+    RMB_CUDA(cudaHostGetDevicePointer((void**)&op->hd_ctrl, op->h_ctrl, 0));
     while ((int)op->it_events.size() < maxorder + 2) {
         cudaEvent_t e;
         RMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1223,7 +1228,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     op->n_launches += 2;
     int k = 0;
     std::vector<long long> act_hist;
-    static const int LOOK = getenv("RMB_LOOKAHEAD") ? std::max(1, std::min(4, atoi(getenv("RMB_LOOKAHEAD")))) : 2;
+    static const int LOOK = getenv("RMB_LOOKAHEAD") ? std::max(1, std::min(4, atoi(getenv("RMB_LOOKAHEAD")))) : 1;
     for (;; ++k) {
         if ((rc = ensure_slab(op, k + 1, st))) return rc;
         cplx* Vk = op->slabs[k];
@@ -1265,7 +1270,7 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
             op->n_launches += 3;
         }
         op->n_iterations++;
-        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl + 4 * k, op->d_ctrl + 4 * k, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        k_publish<<<1, 32, 0, st>>>(op->d_ctrl + 4 * k, op->hd_ctrl + 4 * k, 4);
         RMB_CUDA(cudaEventRecord(op->it_events[k], st));
         // inspect iteration k - LOOK (its kernels have most likely finished by now): the host stays LOOK iterations
         // ahead of the GPU, so its wake-up and launch latencies never leave the GPU idle; the price is LOOK enqueued
@@ -1292,7 +1297,11 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     // state-matvecs actually performed: all states in iteration 0, the survivors of k-1 in iteration k
     op->n_state_matvecs += B;
     for (long long a : act_hist) op->n_state_matvecs += a;
-    if (orders_host) {
+    if (op->pipe_orders) {
+        // host-buffer pipeline: orders of all chunks are gathered on the device and downloaded once at the end
+        k_publish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_order, op->pipe_orders, (int)B);
+        op->pipe_orders += B;
+    } else if (orders_host) {
         // asynchronous: the caller synchronises the stream before reading (rmb_propagate_step documents
         // this; the Python layer reads `last_orders` lazily).  Pageable destinations make the copy
         // synchronous, pinned ones do not.
@@ -1316,7 +1325,12 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
             }
             RMB_CUDA(cudaGetLastError());
         }
-        if (orders_host) std::fill(orders_host, orders_host + nstates, 0);
+        if (op->pipe_orders) {
+            RMB_CUDA(cudaMemsetAsync(op->pipe_orders, 0, sizeof(int) * nstates, st));
+            op->pipe_orders += nstates;
+        } else if (orders_host) {
+            std::fill(orders_host, orders_host + nstates, 0);
+        }
         return RMB_OK;
     }
     int rc = check_field(op);
@@ -1358,10 +1372,14 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         RMB_CUDA(cudaGetLastError());
         op->n_launches++;
         op->n_iterations++;
-        if (orders_host)
+        if (op->pipe_orders) {
+            k_publish<<<(unsigned)((nstates + 255) / 256), 256, 0, st>>>(op->d_order, op->pipe_orders, (int)nstates);
+            op->pipe_orders += nstates;
+        } else if (orders_host) {
             RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * nstates, cudaMemcpyDeviceToHost, st));
+        }
         if (op->defer_error) return RMB_OK;      // rmb_propagate_many checks the flag once at the end
-        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        k_publish<<<1, 32, 0, st>>>(op->d_ctrl, op->hd_ctrl, 1);
         RMB_CUDA(cudaStreamSynchronize(st));
         if (op->h_ctrl[0]) {
             char buf[128];
@@ -1510,7 +1528,7 @@ int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, i
     }
     if (fused) {
         op->defer_error = false;
-        RMB_CUDA(cudaMemcpyAsync(op->h_ctrl, op->d_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        k_publish<<<1, 32, 0, st>>>(op->d_ctrl, op->hd_ctrl, 1);
         RMB_CUDA(cudaStreamSynchronize(st));
         if (op->h_ctrl[0]) result = RMB_ERR_MAXORDER;
     }
@@ -1571,11 +1589,10 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
     }
     // Chunked pipeline: upload of chunk c+1 and download of chunk c-1 overlap the propagation of chunk c
     // (PCIe is full duplex; uploads on s_in, downloads on s_out, kernels on the caller's stream).
-    // chunk count: by bytes (a chunk of >= 48 MB keeps the copy engines efficient; 3-6 chunks hide all but the first
-    // upload and the last download), never below 2 states per chunk
+    // chunk count: by bytes (chunks of >= 16 MB keep the copy engines efficient; up to 6 chunks hide all but the first
+    // upload and the last download: measured on H2S / H2O / OCS, tools/r02_i.sh), never below 2 states per chunk
     const double mbytes = (double)elems * 16.0 / 1e6;
-    int want = (int)std::max(1.0, std::min(6.0, mbytes / 48.0));
-    if (nstates >= 128) want = std::max(want, 3);
+    int want = (int)std::max(1.0, std::min(6.0, mbytes / 16.0));
     if (const char* e = getenv("RMB_HOST_CHUNKS")) want = std::max(1, atoi(e));
     long long cs = (nstates + want - 1) / want;
     cs = std::max<long long>(2, (cs + 1) & ~1LL);
@@ -1607,13 +1624,19 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
         mark(op->s_in);
     }
     int result = RMB_OK;
+    if (nstates > op->pipe_orders_cap) {
+        RMB_CUDA(cudaStreamSynchronize(st));
+        if ((rc = ensure(&op->d_pipe_orders, (size_t)nstates))) return rc;
+        op->pipe_orders_cap = nstates;
+    }
+    op->pipe_orders = op->d_pipe_orders;
     for (int c = 0; c < nchunk; ++c) {
         const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
         RMB_CUDA(cudaStreamWaitEvent(st, op->pipe_events[2 * c], 0));
         rc = propagate_device(op, op->d_stage + c0 * ld, b, ld, make_double2(fac_re, fac_im), tol, maxorder, ph,
-                              skip_krylov, orders_host ? orders_host + c0 : nullptr, st);
+                              skip_krylov, nullptr, st);
         if (rc == RMB_ERR_MAXORDER) result = rc;
-        else if (rc != RMB_OK) return rc;
+        else if (rc != RMB_OK) { op->pipe_orders = nullptr; return rc; }
         for (int o = 0; o < nobs; ++o) {
             rc = rmb_expectation(obs[o], (const double*)(op->d_stage + c0 * ld), b, ld,
                                  (double*)(op->d_expv + (long long)o * nstates + c0), st);
@@ -1626,9 +1649,17 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
                                  cudaMemcpyDeviceToHost, op->s_out));
         mark(op->s_out);
     }
+    op->pipe_orders = nullptr;
+    // small results last, on the download stream (behind the last chunk: nothing on the compute stream ever waits for
+    // the D2H copy engine)
+    RMB_CUDA(cudaEventRecord(op->pipe_events[2 * nchunk], st));
+    RMB_CUDA(cudaStreamWaitEvent(op->s_out, op->pipe_events[2 * nchunk], 0));
     if (nobs > 0)
         RMB_CUDA(cudaMemcpyAsync(expval_host, op->d_expv, sizeof(cplx) * (size_t)nobs * nstates,
-                                 cudaMemcpyDeviceToHost, st));
+                                 cudaMemcpyDeviceToHost, op->s_out));
+    if (orders_host)
+        RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_pipe_orders, sizeof(int) * (size_t)nstates, cudaMemcpyDeviceToHost,
+                                 op->s_out));
     RMB_CUDA(cudaStreamSynchronize(st));
     RMB_CUDA(cudaStreamSynchronize(op->s_out));
     if (trace && !tev.empty()) {

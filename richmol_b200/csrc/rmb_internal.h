@@ -177,7 +177,11 @@ struct rmb_operator {
     double* d_gdiag = nullptr;       // [S][maxorder+1]  <V_i,V_i> (diagonal of the Gram matrix of the Krylov vectors)
     unsigned* d_ticket = nullptr;    // [S]  arrival counter of k_recur_gram's CTAs per state
     int* d_ctrl = nullptr;           // per iteration k: [4k] states still active, [4k+1] maxorder flag
-    int* h_ctrl = nullptr;           // pinned mirror
+    int* h_ctrl = nullptr;           // pinned + mapped mirror, written by k_publish
+    int* hd_ctrl = nullptr;          // its device address
+    int* d_pipe_orders = nullptr;    // host-buffer pipeline: Lanczos orders of all chunks (one download at the end)
+    int* pipe_orders = nullptr;      // write cursor into d_pipe_orders while a pipeline call is in flight, else nullptr
+    long long pipe_orders_cap = 0;
     int nchunk = 0;
     // host staging for the *_host entry point
     rmb::cplx* d_stage = nullptr;

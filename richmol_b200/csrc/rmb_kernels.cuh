@@ -617,6 +617,15 @@ __global__ void k_init_states(int* __restrict__ active, int* __restrict__ order,
     }
 }
 
+// copies n ints, e.g. the control words of a Lanczos iteration into the pinned, mapped host mirror (system-scope fence:
+// visible to the host once the event recorded behind this kernel has completed) -- a kernel instead of a D2H memcpy so
+// that nothing on the compute stream ever queues behind a large download on the copy engine
+__global__ void k_publish(const int* __restrict__ src, int* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    __threadfence_system();
+}
+
 __global__ void k_fill_int(int* p, int v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

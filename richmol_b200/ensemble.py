@@ -65,3 +65,27 @@ def ensemble_expectation(O, vecs_local, group=None):
     if isinstance(local, torch.Tensor):
         return allreduce_sum(local.reshape(1), group)[0]
     return allreduce_sum(np.array([local]), group)[0]
+
+
+def bind_to_gpu_numa(device_index):
+    """Pins the calling process to the CPU cores of the NUMA node the GPU hangs off (NVML's ideal CPU affinity), so
+    that pinned staging buffers are first-touched on that node and host <-> device copies of the per-rank shard do not
+    cross the socket interconnect.  With one process per GPU this is what keeps the host-buffer path (`TDSE.update` on
+    numpy arrays) from collapsing when all GPUs of a box move their shards at once.  Returns the CPU set or None."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device_index]) if vis else int(device_index)
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
