@@ -90,26 +90,28 @@ void rmb_operator_destroy(rmb_operator* op) {
         cudaFree(p.d_coef);
         cudaFree(p.d_fprod);
     }
-    for (auto* s : op->slabs) cudaFree(s);
-    cudaFree(op->d_w);
-    cudaFree(op->d_slab_ptrs);
-    cudaFree(op->d_alpha);
-    cudaFree(op->d_beta);
-    cudaFree(op->d_ccur);
-    cudaFree(op->d_dc);
-    cudaFree(op->d_rinv);
-    cudaFree(op->d_ceff);
-    for (auto e : op->it_events) cudaEventDestroy(e);
-    cudaFree(op->d_active);
-    cudaFree(op->d_order);
-    cudaFree(op->d_pdot);
-    cudaFree(op->d_pnrm);
-    cudaFree(op->d_pconv);
-    cudaFree(op->d_pg0);
-    cudaFree(op->d_gdiag);
-    cudaFree(op->d_ticket);
-    cudaFree(op->d_ctrl);
-    if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
+    for (auto& w : op->wsp) {
+        for (auto* s : w.slabs) cudaFree(s);
+        cudaFree(w.d_w);
+        cudaFree(w.d_slab_ptrs);
+        cudaFree(w.d_alpha);
+        cudaFree(w.d_beta);
+        cudaFree(w.d_ccur);
+        cudaFree(w.d_dc);
+        cudaFree(w.d_rinv);
+        cudaFree(w.d_ceff);
+        for (auto e : w.it_events) cudaEventDestroy(e);
+        cudaFree(w.d_active);
+        cudaFree(w.d_order);
+        cudaFree(w.d_pdot);
+        cudaFree(w.d_pnrm);
+        cudaFree(w.d_pconv);
+        cudaFree(w.d_pg0);
+        cudaFree(w.d_gdiag);
+        cudaFree(w.d_ticket);
+        cudaFree(w.d_ctrl);
+        if (w.h_ctrl) cudaFreeHost(w.h_ctrl);
+    }
     cudaFree(op->d_stage);
     cudaFree(op->d_pipe_orders);
     cudaFree(op->d_expv);
@@ -932,9 +934,37 @@ struct MvEpilogue {
     bool use_lin = false;            // sliding-window kernel for linear rotors (npart = nblocks)
 };
 
+// Field-dependent tables of the matvec kernels, rebuilt on `st` after a field update: the entry lists of the sliding-window
+// kernel, or the surviving-diagonal counts in the descriptors of the tiled / DMMA kernels.  launch_matvec calls it; the
+// host-buffer pipeline calls it once on the caller's stream before it forks onto several compute streams.
+static int matvec_prep(rmb_operator* op, cudaStream_t st, bool use_lin) {
+    if (use_lin && op->lin_ok) {
+        if (op->lin_flat_dirty) {
+            lin_update_bound(op);
+            k_lin_entries<<<(unsigned)op->nblocks, 128, 0, st>>>(
+                op->nblocks, op->lin_NS, (unsigned)(op->lin_T * op->lin_dm_max * 16), op->d_blk_begin, op->d_blk_dm,
+                op->d_prod_ket, op->d_prods, op->d_tab_mask, (const MfEntry*)op->d_ent_cent, op->d_kpool,
+                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val);
+            op->lin_flat_dirty = false;
+            op->n_launches++;
+        }
+    } else if (op->nnz_dirty && op->ngdesc > 0) {
+        // surviving diagonals per (item, product) descriptor of the tiled and DMMA kernels, after a field update
+        k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask, op->d_tab_cplx);
+        op->nnz_dirty = false;
+        op->n_launches++;
+    }
+    RMB_CUDA(cudaGetLastError());
+    return RMB_OK;
+}
+
 static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nstates, long long ldx,
                          long long ldy, const int* active, cudaStream_t st, const MvEpilogue& ep = MvEpilogue()) {
     if ((op->nitems == 0 && op->nitems2 == 0 && op->nitemsG == 0) || nstates == 0) return RMB_OK;
+    {
+        const int rcp = matvec_prep(op, st, ep.use_lin);
+        if (rcp) return rcp;
+    }
     const int S = op->matvec_S;
     const int zstride = (int)(op->matvec_smem / (S * sizeof(cplx)));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -954,21 +984,12 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         la.W = op->lin_W;
         la.dms = op->lin_dm_max;
         la.NS = op->lin_NS;
-        if (op->lin_flat_dirty) lin_update_bound(op);
         la.NB = op->lin_NB;
         la.ebuf_elems = op->lin_ebuf_cur;
         la.blk = (const LinBlk*)op->d_lin_blk;
         la.flat = (const LinEnt*)op->d_lin_flat;
         la.val = op->d_lin_val;
         const int T = op->lin_T;
-        if (op->lin_flat_dirty) {
-            k_lin_entries<<<(unsigned)op->nblocks, 128, 0, st>>>(
-                op->nblocks, op->lin_NS, (unsigned)(T * op->lin_dm_max * 16), op->d_blk_begin, op->d_blk_dm,
-                op->d_prod_ket, op->d_prods, op->d_tab_mask, (const MfEntry*)op->d_ent_cent, op->d_kpool,
-                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val);
-            op->lin_flat_dirty = false;
-            op->n_launches++;
-        }
         const unsigned grid = (unsigned)((nstates + T - 1) / T);
         if (op->lin_g1 && T == 8)
             k_matvec_lin<8, true><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
@@ -990,12 +1011,6 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         }
         op->n_matvec_launches++;
         return RMB_OK;
-    }
-    if (op->nnz_dirty && op->ngdesc > 0) {
-        // surviving diagonals per (item, product) descriptor of the tiled and DMMA kernels, after a field update
-        k_fill_nnz<<<(unsigned)((op->ngdesc + 255) / 256), 256, 0, st>>>(op->ngdesc, (ProdS*)op->d_gdesc, op->d_tab_mask, op->d_tab_cplx);
-        op->nnz_dirty = false;
-        op->n_launches++;
     }
     if (op->nitems2 > 0) {
         // work units (item, first state) for this batch size; rebuilt only when the size changes
@@ -1114,99 +1129,167 @@ static int ensure(T** p, size_t count) {
     return RMB_OK;
 }
 
+// speculative enqueue: the next call starts with as many iterations as this one needed
+static inline void commit_spec(rmb_operator* op) {
+    op->spec_guess = std::max(1, op->spec_seen);
+    op->spec_seen = 0;
+}
+
 // the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
 static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 + op->nitemsG > 0; }
-static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 + op->nitemsG : op->nchunk; }
+static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 + op->nitemsG : op->W->nchunk; }
 
 // (re)allocate the per-state small arrays and the product vector for `cap` states
 static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
-    if (cap <= op->ws_states && maxorder <= op->ws_maxorder && op->d_w) return RMB_OK;
-    cap = std::max(cap, op->ws_states);
-    maxorder = std::max(maxorder, op->ws_maxorder);
+    if (cap <= op->W->ws_states && maxorder <= op->W->ws_maxorder && op->W->d_w) return RMB_OK;
+    cap = std::max(cap, op->W->ws_states);
+    maxorder = std::max(maxorder, op->W->ws_maxorder);
     RMB_CUDA(cudaDeviceSynchronize());
-    for (auto* s : op->slabs) cudaFree(s);
-    op->slabs.clear();
-    op->slab_ptrs_uploaded = 0;
-    op->nchunk = nchunks(op->np);
+    for (auto* s : op->W->slabs) cudaFree(s);
+    op->W->slabs.clear();
+    op->W->slab_ptrs_uploaded = 0;
+    op->W->nchunk = nchunks(op->np);
     int rc;
     const size_t vec = (size_t)cap * (size_t)op->np;
-    const size_t np = (size_t)std::max({op->nchunk, op->nitems2 + op->nitemsG, op->lin_npart});
-    if ((rc = ensure(&op->d_w, vec))) return rc;
-    RMB_CUDA(cudaMemset(op->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
-    if ((rc = ensure(&op->d_alpha, (size_t)cap * maxorder))) return rc;
-    if ((rc = ensure(&op->d_beta, (size_t)cap * (maxorder + 1)))) return rc;
-    if ((rc = ensure(&op->d_rinv, (size_t)cap * (maxorder + 1)))) return rc;
-    if ((rc = ensure(&op->d_ccur, (size_t)cap * maxorder))) return rc;
-    if ((rc = ensure(&op->d_ceff, (size_t)cap * maxorder))) return rc;
-    if ((rc = ensure(&op->d_dc, (size_t)cap * maxorder))) return rc;
-    if ((rc = ensure(&op->d_active, (size_t)cap))) return rc;
-    if ((rc = ensure(&op->d_order, (size_t)cap))) return rc;
-    if ((rc = ensure(&op->d_pdot, (size_t)cap * np))) return rc;
-    if ((rc = ensure(&op->d_pnrm, (size_t)cap * op->nchunk))) return rc;
-    if ((rc = ensure(&op->d_pconv, (size_t)cap * op->nchunk))) return rc;
-    if ((rc = ensure(&op->d_pg0, (size_t)cap * op->nchunk))) return rc;
-    if ((rc = ensure(&op->d_gdiag, (size_t)cap * (maxorder + 1)))) return rc;
-    if ((rc = ensure(&op->d_ticket, (size_t)cap))) return rc;
-    RMB_CUDA(cudaMemset(op->d_ticket, 0, std::max<size_t>(1, (size_t)cap) * sizeof(unsigned)));
-    if ((rc = ensure(&op->d_ctrl, (size_t)4 * (maxorder + 2)))) return rc;
+    const size_t np = (size_t)std::max({op->W->nchunk, op->nitems2 + op->nitemsG, op->lin_npart});
+    if ((rc = ensure(&op->W->d_w, vec))) return rc;
+    RMB_CUDA(cudaMemset(op->W->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
+    if ((rc = ensure(&op->W->d_alpha, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->W->d_beta, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->W->d_rinv, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->W->d_ccur, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->W->d_ceff, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->W->d_dc, (size_t)cap * maxorder))) return rc;
+    if ((rc = ensure(&op->W->d_active, (size_t)cap))) return rc;
+    if ((rc = ensure(&op->W->d_order, (size_t)cap))) return rc;
+    if ((rc = ensure(&op->W->d_pdot, (size_t)cap * np))) return rc;
+    if ((rc = ensure(&op->W->d_pnrm, (size_t)cap * op->W->nchunk))) return rc;
+    if ((rc = ensure(&op->W->d_pconv, (size_t)cap * op->W->nchunk))) return rc;
+    if ((rc = ensure(&op->W->d_pg0, (size_t)cap * op->W->nchunk))) return rc;
+    if ((rc = ensure(&op->W->d_gdiag, (size_t)cap * (maxorder + 1)))) return rc;
+    if ((rc = ensure(&op->W->d_ticket, (size_t)cap))) return rc;
+    RMB_CUDA(cudaMemset(op->W->d_ticket, 0, std::max<size_t>(1, (size_t)cap) * sizeof(unsigned)));
+    if ((rc = ensure(&op->W->d_ctrl, (size_t)4 * (maxorder + 2)))) return rc;
     // pinned AND mapped: the control words are published by a one-warp kernel (k_publish) instead of a D2H memcpy on the
     // compute stream, which would queue behind any large download in flight on the same copy engine (the host-buffer
     // pipeline's own downloads serialised every chunk's Lanczos loop that way)
-    if (op->h_ctrl) cudaFreeHost(op->h_ctrl);
-    RMB_CUDA(cudaHostAlloc((void**)&op->h_ctrl, sizeof(int) * 4 * (maxorder + 2), cudaHostAllocMapped));
-    RMB_CUDA(cudaHostGetDevicePointer((void**)&op->hd_ctrl, op->h_ctrl, 0));
-    while ((int)op->it_events.size() < maxorder + 2) {
+    if (op->W->h_ctrl) cudaFreeHost(op->W->h_ctrl);
+    RMB_CUDA(cudaHostAlloc((void**)&op->W->h_ctrl, sizeof(int) * 4 * (maxorder + 2), cudaHostAllocMapped));
+    RMB_CUDA(cudaHostGetDevicePointer((void**)&op->W->hd_ctrl, op->W->h_ctrl, 0));
+    while ((int)op->W->it_events.size() < maxorder + 2) {
         cudaEvent_t e;
         RMB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        op->it_events.push_back(e);
+        op->W->it_events.push_back(e);
     }
-    op->ws_states = cap;
-    op->ws_maxorder = maxorder;
+    op->W->ws_states = cap;
+    op->W->ws_maxorder = maxorder;
     return RMB_OK;
 }
 
 static int ensure_slab(rmb_operator* op, int k, cudaStream_t st) {
-    while ((int)op->slabs.size() <= k) {
+    while ((int)op->W->slabs.size() <= k) {
         cplx* p = nullptr;
-        RMB_CUDA(cudaMalloc((void**)&p, (size_t)op->ws_states * (size_t)op->np * sizeof(cplx)));
-        RMB_CUDA(cudaMemsetAsync(p, 0, (size_t)op->ws_states * (size_t)op->np * sizeof(cplx), st));
-        op->slabs.push_back(p);
+        RMB_CUDA(cudaMalloc((void**)&p, (size_t)op->W->ws_states * (size_t)op->np * sizeof(cplx)));
+        RMB_CUDA(cudaMemsetAsync(p, 0, (size_t)op->W->ws_states * (size_t)op->np * sizeof(cplx), st));
+        op->W->slabs.push_back(p);
     }
-    if (op->slab_ptrs_cap < (int)op->slabs.size() || !op->d_slab_ptrs) {
+    if (op->W->slab_ptrs_cap < (int)op->W->slabs.size() || !op->W->d_slab_ptrs) {
         RMB_CUDA(cudaStreamSynchronize(st));
-        if (op->d_slab_ptrs) cudaFree(op->d_slab_ptrs);
-        op->slab_ptrs_cap = std::max(16, (int)op->slabs.size() * 2);
-        op->slab_ptrs_uploaded = 0;
-        RMB_CUDA(cudaMalloc((void**)&op->d_slab_ptrs, op->slab_ptrs_cap * sizeof(cplx*)));
+        if (op->W->d_slab_ptrs) cudaFree(op->W->d_slab_ptrs);
+        op->W->slab_ptrs_cap = std::max(16, (int)op->W->slabs.size() * 2);
+        op->W->slab_ptrs_uploaded = 0;
+        RMB_CUDA(cudaMalloc((void**)&op->W->d_slab_ptrs, op->W->slab_ptrs_cap * sizeof(cplx*)));
     }
-    if (op->slab_ptrs_uploaded != (int)op->slabs.size()) {
+    if (op->W->slab_ptrs_uploaded != (int)op->W->slabs.size()) {
         RMB_CUDA(cudaStreamSynchronize(st));   // kernels in flight read the table; slabs.data() is pageable
-        RMB_CUDA(cudaMemcpyAsync(op->d_slab_ptrs, op->slabs.data(), op->slabs.size() * sizeof(cplx*),
+        RMB_CUDA(cudaMemcpyAsync(op->W->d_slab_ptrs, op->W->slabs.data(), op->W->slabs.size() * sizeof(cplx*),
                                  cudaMemcpyHostToDevice, st));
         RMB_CUDA(cudaStreamSynchronize(st));
-        op->slab_ptrs_uploaded = (int)op->slabs.size();
+        op->W->slab_ptrs_uploaded = (int)op->W->slabs.size();
     }
     return RMB_OK;
 }
 
-// One sub-batch of states through the literal Lanczos loop of tdse.py:417-486.
+// One sub-batch of states through the literal Lanczos loop of tdse.py:417-486, in two halves so that several
+// batches (the chunks of the host-buffer pipeline, each on its own stream and workspace) can be in flight at once:
 //
-// Launches per iteration: matvec (+ fused scale and <w,V_k> partials), k_small_a (alpha, small
-// exponential), k_recur_conv (three-term recurrence + convergence metric), k_small_b (beta, stop rule,
-// zero-beta fallback).  The host does not block on every iteration: the control word of iteration k
-// is copied back asynchronously and inspected after iteration k+1 has been enqueued, so the GPU
-// never idles on the host; the price is one enqueued iteration in which every state is inactive.
-static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol,
-                         int maxorder, const cplx* ph, int* orders_host, cudaStream_t st,
-                         bool* hit_maxorder) {
+//   lanczos_begin   phase/scatter, then iterations 0..guess enqueued WITHOUT asking the device anything (`guess` = the
+//                   iteration at which the previous call of this operator ran out of active states: fields change
+//                   slowly from step to step, so the loop length rarely changes);
+//   lanczos_finish  reads the control words (one synchronisation), continues one iteration at a time if states are
+//                   still active (host one iteration ahead of the device), then the final combination.
+//
+// Launches per iteration: matvec (+ fused scale and <w,V_k> partials) and k_recur_gram (recurrence, alpha/beta, small
+// exponential, convergence metric, stop rule); beyond RMB_GRAM_KMAX iterations the explicit evaluation with k_small_a /
+// k_recur_conv / k_small_b.  An iteration enqueued after every state has retired costs a few microseconds (every
+// kernel returns on the `active` flags).
+static int lz_enqueue_iter(rmb_operator* op, int k) {
+    Workspace* W = op->W;
+    LzRun& r = W->run;
+    cudaStream_t st = r.st;
+    const long long n = op->n, np = op->np, B = r.B;
+    const int nch = W->nchunk;
+    const int ts = W->ws_maxorder, bs = W->ws_maxorder + 1;
+    const dim3 vgrid((unsigned)nch, (unsigned)B);
+    static const bool gram = !(getenv("RMB_GRAM") && atoi(getenv("RMB_GRAM")) == 0);
+    int rc;
+    if ((rc = ensure_slab(op, k + 1, st))) return rc;
+    cplx* Vk = W->slabs[k];
+    MvEpilogue ep;
+    if (r.fused) {
+        ep.scale = W->d_rinv + k;
+        ep.scale_stride = bs;
+        ep.pdot = W->d_pdot;
+        ep.npart = r.npart;
+        ep.use_lin = r.lin;
+    }
+    if ((rc = launch_matvec(op, Vk, W->d_w, B, np, np, W->d_active, st, ep))) return rc;
+    if (!r.fused) {
+        // some bra blocks went through the scalar kernel, which has no epilogue: scale the product
+        // (w = rinv_k * H slab_k) and form the partial dots in separate passes
+        k_scale_rows<<<vgrid, VEC_THREADS, 0, st>>>(W->d_w, np, np, W->d_rinv + k, bs, W->d_active);
+        k_dot<<<vgrid, VEC_THREADS, 0, st>>>(W->d_w, Vk, np, np, W->d_pdot, r.npart, W->d_active);
+        op->n_launches += 2;
+    }
+    if (gram && k < RMB_GRAM_KMAX) {
+        // one launch: recurrence + (last CTA per state) alpha/beta, small exponential, Gram-diagonal
+        // convergence metric, stop rule, zero-beta fallback
+        k_recur_gram<<<dim3((unsigned)r.nsl_p, (unsigned)B), VEC_THREADS, 0, st>>>(
+            W->d_w, W->d_slab_ptrs, np, np, W->d_pdot, r.npart, W->d_alpha, W->d_beta, W->d_rinv, W->d_gdiag, ts, bs, k,
+            r.fac, W->d_ccur, W->d_ceff, W->d_pnrm, W->d_pg0, r.nsl_p, r.cps_p, nch, W->d_ticket, r.tol, r.maxorder,
+            W->d_active, W->d_order, W->d_ctrl, op->d_pmap, n);
+        op->n_launches += 1;
+    } else {
+        // explicit evaluation of sum |u_k - u_{k-1}|^2 over the Krylov history (many vectors: the Gram matrix is no
+        // longer close to diagonal once the three-term recurrence loses orthogonality)
+        k_small_a<<<(unsigned)B, 32, 0, st>>>(W->d_pdot, r.npart, W->d_alpha, W->d_beta, W->d_rinv, ts, bs, k, r.fac,
+                                              W->d_ccur, W->d_ceff, W->d_dc, W->d_active);
+        k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(W->d_w, W->d_slab_ptrs, np, np, W->d_alpha, W->d_beta, W->d_rinv,
+                                                    W->d_dc, ts, bs, k, W->d_pnrm, W->d_pconv, nch, W->d_active);
+        k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(W->d_pnrm, W->d_pconv, nch, W->d_beta, W->d_rinv, bs, k, r.tol,
+                                                       r.maxorder, W->d_active, W->d_order, W->d_ctrl, W->d_slab_ptrs, np,
+                                                       n, op->d_pmap);
+        op->n_launches += 3;
+    }
+    op->n_iterations++;
+    // control words of the iteration -> pinned, mapped host mirror (a kernel, not a memcpy: see ensure_workspace)
+    k_publish<<<1, 32, 0, st>>>(W->d_ctrl + 4 * k, W->hd_ctrl + 4 * k, 4);
+    RMB_CUDA(cudaEventRecord(W->it_events[k], st));
+    r.k_last = k;
+    return RMB_OK;
+}
+
+static int lanczos_begin(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol, int maxorder,
+                         const cplx* ph, cudaStream_t st) {
+    Workspace* W = op->W;
+    LzRun& r = W->run;
     const long long n = op->n, np = op->np;
-    const int nch = op->nchunk;
-    const dim3 vgrid((unsigned)nch, (unsigned)B);          // padded vectors
-    const dim3 ugrid((unsigned)nchunks(n), (unsigned)B);   // user-layout vectors
-    const int ts = op->ws_maxorder, bs = op->ws_maxorder + 1;
-    const bool lin = op->lin_ok && B >= 4 * op->lin_T;      // large batches of linear rotors: sliding window
-    const bool fused = lin || fused_dot(op);
-    const int npart = lin ? op->lin_npart : dot_parts(op);
+    const int nch = W->nchunk;
+    const int bs = W->ws_maxorder + 1;
+    r.psi = psi; r.B = B; r.ld = ld; r.fac = fac; r.tol = tol; r.maxorder = maxorder; r.ph = ph; r.st = st;
+    r.lin = op->lin_ok && B >= 4 * op->lin_T;      // large batches of linear rotors: sliding window
+    r.fused = r.lin || fused_dot(op);
+    r.npart = r.lin ? op->lin_npart : dot_parts(op);
     // sliced grids of the vector kernels: a CTA walks `cps` consecutive chunks of one state (~12 CTAs per SM in total)
     auto slices = [&](int nchunk_, int* nsl_, int* cps_) {
         const long long want = std::max<long long>(1, (12LL * op->num_sms + B - 1) / B);
@@ -1214,84 +1297,58 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
         *cps_ = (nchunk_ + nsl0 - 1) / nsl0;
         *nsl_ = (nchunk_ + *cps_ - 1) / *cps_;
     };
-    int nsl_p, cps_p, nsl_u, cps_u;
-    slices(nch, &nsl_p, &cps_p);
-    slices(nchunks(n), &nsl_u, &cps_u);
-    static const bool gram = !(getenv("RMB_GRAM") && atoi(getenv("RMB_GRAM")) == 0);
+    slices(nch, &r.nsl_p, &r.cps_p);
+    slices(nchunks(n), &r.nsl_u, &r.cps_u);
     int rc;
     if ((rc = ensure_slab(op, 2, st))) return rc;
-    RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
-    k_init_states<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_active, op->d_order, op->d_rinv,
-                                                               op->d_beta, bs, (int)B);
-    k_phase_init_s<<<dim3((unsigned)nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(psi, ld, ph, op->slabs[0], np, n, op->d_pmap,
-                                                                                cps_u, nchunks(n));
+    RMB_CUDA(cudaMemsetAsync(W->d_ctrl, 0, sizeof(int) * 4 * (maxorder + 2), st));
+    k_init_states<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(W->d_active, W->d_order, W->d_rinv, W->d_beta, bs, (int)B);
+    k_phase_init_s<<<dim3((unsigned)r.nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(psi, ld, ph, W->slabs[0], np, n, op->d_pmap,
+                                                                                  r.cps_u, nchunks(n));
     op->n_launches += 2;
-    int k = 0;
+    static const bool spec = !(getenv("RMB_SPEC") && atoi(getenv("RMB_SPEC")) == 0);
+    const int guess = spec ? std::min(op->spec_guess, maxorder - 1) : 0;
+    for (int k = 0; k <= std::max(0, guess); ++k)
+        if ((rc = lz_enqueue_iter(op, k))) return rc;
+    r.open = true;
+    return RMB_OK;
+}
+
+static int lanczos_finish(rmb_operator* op, int* orders_host, bool* hit_maxorder) {
+    Workspace* W = op->W;
+    LzRun& r = W->run;
+    cudaStream_t st = r.st;
+    const long long n = op->n, np = op->np, B = r.B;
+    const int ts = W->ws_maxorder;
+    int rc;
+    r.open = false;
+    // control words of everything enqueued so far
+    int checked = -1, stop = -1;
     std::vector<long long> act_hist;
-    static const int LOOK = getenv("RMB_LOOKAHEAD") ? std::max(1, std::min(4, atoi(getenv("RMB_LOOKAHEAD")))) : 1;
-    for (;; ++k) {
-        if ((rc = ensure_slab(op, k + 1, st))) return rc;
-        cplx* Vk = op->slabs[k];
-        MvEpilogue ep;
-        if (fused) {
-            ep.scale = op->d_rinv + k;
-            ep.scale_stride = bs;
-            ep.pdot = op->d_pdot;
-            ep.npart = npart;
-            ep.use_lin = lin;
+    auto check_to = [&](int upto) -> int {
+        RMB_CUDA(cudaEventSynchronize(W->it_events[upto]));
+        while (checked < upto && stop < 0) {
+            ++checked;
+            act_hist.push_back(W->h_ctrl[4 * checked]);
+            if (W->h_ctrl[4 * checked + 1]) *hit_maxorder = true;
+            if (W->h_ctrl[4 * checked] == 0) stop = checked;
         }
-        if ((rc = launch_matvec(op, Vk, op->d_w, B, np, np, op->d_active, st, ep))) return rc;
-        if (!fused) {
-            // some bra blocks went through the scalar kernel, which has no epilogue: scale the product
-            // (w = rinv_k * H slab_k) and form the partial dots in separate passes
-            k_scale_rows<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, np, np, op->d_rinv + k, bs, op->d_active);
-            k_dot<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, Vk, np, np, op->d_pdot, npart, op->d_active);
-            op->n_launches += 2;
-        }
-        if (gram && k < RMB_GRAM_KMAX) {
-            // one launch: recurrence + (last CTA per state) alpha/beta, small exponential, Gram-diagonal
-            // convergence metric, stop rule, zero-beta fallback
-            k_recur_gram<<<dim3((unsigned)nsl_p, (unsigned)B), VEC_THREADS, 0, st>>>(
-                op->d_w, op->d_slab_ptrs, np, np, op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, op->d_gdiag,
-                ts, bs, k, fac, op->d_ccur, op->d_ceff, op->d_pnrm, op->d_pg0, nsl_p, cps_p, nch, op->d_ticket, tol,
-                maxorder, op->d_active, op->d_order, op->d_ctrl, op->d_pmap, n);
-            op->n_launches += 1;
-        } else {
-            // explicit evaluation of sum |u_k - u_{k-1}|^2 over the Krylov history (many vectors: the Gram matrix is no
-            // longer close to diagonal once the three-term recurrence loses orthogonality)
-            k_small_a<<<(unsigned)B, 32, 0, st>>>(op->d_pdot, npart, op->d_alpha, op->d_beta, op->d_rinv, ts, bs, k,
-                                                  fac, op->d_ccur, op->d_ceff, op->d_dc, op->d_active);
-            k_recur_conv<<<vgrid, VEC_THREADS, 0, st>>>(op->d_w, op->d_slab_ptrs, np, np, op->d_alpha, op->d_beta,
-                                                        op->d_rinv, op->d_dc, ts, bs, k, op->d_pnrm, op->d_pconv,
-                                                        nch, op->d_active);
-            k_small_b<<<(unsigned)B, VEC_THREADS, 0, st>>>(op->d_pnrm, op->d_pconv, nch, op->d_beta, op->d_rinv, bs, k,
-                                                           tol, maxorder, op->d_active, op->d_order, op->d_ctrl,
-                                                           op->d_slab_ptrs, np, n, op->d_pmap);
-            op->n_launches += 3;
-        }
-        op->n_iterations++;
-        k_publish<<<1, 32, 0, st>>>(op->d_ctrl + 4 * k, op->hd_ctrl + 4 * k, 4);
-        RMB_CUDA(cudaEventRecord(op->it_events[k], st));
-        // inspect iteration k - LOOK (its kernels have most likely finished by now): the host stays LOOK iterations
-        // ahead of the GPU, so its wake-up and launch latencies never leave the GPU idle; the price is LOOK enqueued
-        // iterations in which every state is inactive (a few microseconds each)
-        if (k >= LOOK) {
-            RMB_CUDA(cudaEventSynchronize(op->it_events[k - LOOK]));
-            act_hist.push_back(op->h_ctrl[4 * (k - LOOK)]);
-            if (op->h_ctrl[4 * (k - LOOK) + 1]) *hit_maxorder = true;
-            if (op->h_ctrl[4 * (k - LOOK)] == 0) break;
-        }
-        if (k + 1 >= maxorder + 1) {   // every state has been retired by iteration maxorder - 1: read what is outstanding
-            RMB_CUDA(cudaEventSynchronize(op->it_events[k]));
-            for (int j = std::max(0, k - LOOK + 1); j <= k; ++j) {
-                act_hist.push_back(op->h_ctrl[4 * j]);
-                if (op->h_ctrl[4 * j + 1]) *hit_maxorder = true;
-            }
-            break;
-        }
+        return RMB_OK;
+    };
+    if ((rc = check_to(r.k_last))) return rc;
+    // states still active: continue, the host one iteration ahead of the device (its wake-up and launch latencies stay
+    // hidden; the price is one enqueued iteration in which every state is inactive)
+    while (stop < 0 && checked < r.maxorder) {
+        if (r.k_last <= checked && r.k_last < r.maxorder)
+            if ((rc = lz_enqueue_iter(op, r.k_last + 1))) return rc;
+        if (r.k_last == checked + 1 && r.k_last < r.maxorder)
+            if ((rc = lz_enqueue_iter(op, r.k_last + 1))) return rc;
+        if ((rc = check_to(checked + 1))) return rc;
     }
-    k_combine_s<<<dim3((unsigned)nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(op->d_slab_ptrs, np, n, op->d_ceff, ts, op->d_order,
-                                                                             ph, psi, ld, op->d_pmap, cps_u, nchunks(n));
+    if (stop >= 0) op->spec_seen = std::max(op->spec_seen, stop);
+    k_combine_s<<<dim3((unsigned)r.nsl_u, (unsigned)B), VEC_THREADS, 0, st>>>(W->d_slab_ptrs, np, n, W->d_ceff, ts, W->d_order,
+                                                                               r.ph, r.psi, r.ld, op->d_pmap, r.cps_u,
+                                                                               nchunks(n));
     op->n_launches++;
     RMB_CUDA(cudaGetLastError());
     // state-matvecs actually performed: all states in iteration 0, the survivors of k-1 in iteration k
@@ -1299,15 +1356,23 @@ static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld,
     for (long long a : act_hist) op->n_state_matvecs += a;
     if (op->pipe_orders) {
         // host-buffer pipeline: orders of all chunks are gathered on the device and downloaded once at the end
-        k_publish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(op->d_order, op->pipe_orders, (int)B);
+        k_publish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(W->d_order, op->pipe_orders, (int)B);
         op->pipe_orders += B;
     } else if (orders_host) {
         // asynchronous: the caller synchronises the stream before reading (rmb_propagate_step documents
         // this; the Python layer reads `last_orders` lazily).  Pageable destinations make the copy
         // synchronous, pinned ones do not.
-        RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        RMB_CUDA(cudaMemcpyAsync(orders_host, W->d_order, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     }
     return RMB_OK;
+}
+
+static int lanczos_batch(rmb_operator* op, cplx* psi, long long B, long long ld, cplx fac, double tol,
+                         int maxorder, const cplx* ph, int* orders_host, cudaStream_t st,
+                         bool* hit_maxorder) {
+    int rc = lanczos_begin(op, psi, B, ld, fac, tol, maxorder, ph, st);
+    if (rc) return rc;
+    return lanczos_finish(op, orders_host, hit_maxorder);
 }
 
 static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long long ld, cplx fac,
@@ -1344,7 +1409,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         (long long)nstates * n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30)) {
         if ((rc = ensure_workspace(op, nstates, maxorder))) return rc;
         if ((rc = ensure_slab(op, maxorder, st))) return rc;
-        if (!op->defer_error) RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
+        if (!op->defer_error) RMB_CUDA(cudaMemsetAsync(op->W->d_ctrl, 0, sizeof(int) * 4, st));
         FusedArgs fa;
         fa.n = n;
         fa.row_blk = op->d_row_blk;
@@ -1357,15 +1422,15 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         fa.kpool = op->d_kpool;
         fa.k_complex = op->k_complex ? 1 : 0;
         fa.nprod = op->nprod;
-        fa.slabs = op->d_slab_ptrs;
+        fa.slabs = op->W->d_slab_ptrs;
         fa.fac = fac;
         fa.tol = tol;
         fa.maxorder = maxorder;
         fa.ph = ph;
         fa.psi = psi;
         fa.ld = ld;
-        fa.order = op->d_order;
-        fa.ctrl = op->d_ctrl;
+        fa.order = op->W->d_order;
+        fa.ctrl = op->W->d_ctrl;
         // the history slabs are indexed [slab][state * n + i] with the leading dimension of this batch
         k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS,
                           (size_t)3 * n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd), st>>>(fa, nstates);
@@ -1373,15 +1438,15 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         op->n_launches++;
         op->n_iterations++;
         if (op->pipe_orders) {
-            k_publish<<<(unsigned)((nstates + 255) / 256), 256, 0, st>>>(op->d_order, op->pipe_orders, (int)nstates);
+            k_publish<<<(unsigned)((nstates + 255) / 256), 256, 0, st>>>(op->W->d_order, op->pipe_orders, (int)nstates);
             op->pipe_orders += nstates;
         } else if (orders_host) {
-            RMB_CUDA(cudaMemcpyAsync(orders_host, op->d_order, sizeof(int) * nstates, cudaMemcpyDeviceToHost, st));
+            RMB_CUDA(cudaMemcpyAsync(orders_host, op->W->d_order, sizeof(int) * nstates, cudaMemcpyDeviceToHost, st));
         }
         if (op->defer_error) return RMB_OK;      // rmb_propagate_many checks the flag once at the end
-        k_publish<<<1, 32, 0, st>>>(op->d_ctrl, op->hd_ctrl, 1);
+        k_publish<<<1, 32, 0, st>>>(op->W->d_ctrl, op->W->hd_ctrl, 1);
         RMB_CUDA(cudaStreamSynchronize(st));
-        if (op->h_ctrl[0]) {
+        if (op->W->h_ctrl[0]) {
             char buf[128];
             snprintf(buf, sizeof(buf), "Lanczos reached maximum order of '%d' without convergence", maxorder);
             set_error(buf);
@@ -1390,22 +1455,22 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         return RMB_OK;
     }
     // sub-batch size from the workspace budget: the product vector and ~15 Krylov vectors per state
-    long long bc = op->ws_states;
+    long long bc = op->W->ws_states;
     if (bc < std::min<long long>(nstates, 65535)) {
         // more states than the workspace holds: (re)size it from the budget (rare: first call / larger batch)
         long long budget = op->ws_budget;
         if (budget <= 0) {
             size_t fr = 0, tot = 0;
             RMB_CUDA(cudaMemGetInfo(&fr, &tot));
-            long long held = (long long)(op->slabs.size() + 1) * op->ws_states * op->np * (long long)sizeof(cplx);
+            long long held = (long long)(op->W->slabs.size() + 1) * op->W->ws_states * op->np * (long long)sizeof(cplx);
             budget = (long long)(0.4 * (double)(fr + (size_t)held));
         }
         const long long per_state = 16LL * op->np * (long long)sizeof(cplx);
-        bc = std::max({1LL, op->ws_states, std::min({(long long)nstates, budget / per_state, 65535LL})});
+        bc = std::max({1LL, op->W->ws_states, std::min({(long long)nstates, budget / per_state, 65535LL})});
     }
     bc = std::max(1LL, std::min(bc, (long long)nstates));
     if ((rc = ensure_workspace(op, bc, maxorder))) return rc;
-    bc = std::min<long long>(op->ws_states, nstates);
+    bc = std::min<long long>(op->W->ws_states, nstates);
     bool hit = false;
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, nstates - s0);
@@ -1425,7 +1490,7 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
 // scratch for the entry points that take user-layout vectors: one padded slab + the product vector
 static int scratch_for(rmb_operator* op, long long nstates, cudaStream_t st) {
     int rc;
-    if (op->ws_states == 0) {
+    if (op->W->ws_states == 0) {
         const long long cap = std::max<long long>(1, (1LL << 30) / (op->np * (long long)sizeof(cplx)));
         if ((rc = ensure_workspace(op, std::min<long long>({nstates, cap, 65535LL}), 1))) return rc;
     }
@@ -1447,17 +1512,17 @@ int32_t rmb_matvec(rmb_operator* op, const double* x_dev, double* y_dev, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (nstates == 0) return RMB_OK;
     if ((rc = scratch_for(op, nstates, st))) return rc;
-    const long long bc = op->ws_states, n = op->n, np = op->np;
+    const long long bc = op->W->ws_states, n = op->n, np = op->np;
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, (long long)nstates - s0);
         const dim3 ugrid((unsigned)nchunks(n), (unsigned)b);
         // user layout -> padded scratch, product, back
-        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)x_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
+        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)x_dev + s0 * ld, ld, nullptr, op->W->slabs[0], np, n,
                                                     op->d_pmap);
         MvEpilogue epm;
         epm.use_lin = op->lin_ok && b >= 4 * op->lin_T;
-        if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st, epm))) return rc;
-        k_unpad<<<ugrid, VEC_THREADS, 0, st>>>(op->d_w, np, (cplx*)y_dev + s0 * ld, ld, n, op->d_pmap);
+        if ((rc = launch_matvec(op, op->W->slabs[0], op->W->d_w, b, np, np, nullptr, st, epm))) return rc;
+        k_unpad<<<ugrid, VEC_THREADS, 0, st>>>(op->W->d_w, np, (cplx*)y_dev + s0 * ld, ld, n, op->d_pmap);
         op->n_launches += 2;
         op->n_state_matvecs += b;
     }
@@ -1472,8 +1537,10 @@ int32_t rmb_propagate_step(rmb_operator* op, double* psi_dev, int64_t nstates, i
         set_error("propagate_step: bad arguments");
         return RMB_ERR_INVALID;
     }
-    return propagate_device(op, (cplx*)psi_dev, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder,
-                            (const cplx*)h0phase_dev, skip_krylov, orders_host, (cudaStream_t)stream);
+    const int rc = propagate_device(op, (cplx*)psi_dev, nstates, ld, make_double2(fac_re, fac_im), tol, maxorder,
+                                    (const cplx*)h0phase_dev, skip_krylov, orders_host, (cudaStream_t)stream);
+    commit_spec(op);
+    return rc;
 }
 
 int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, int64_t ld, int32_t nsteps,
@@ -1501,7 +1568,7 @@ int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, i
                        (long long)nstates * op->n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30);
     if (fused) {
         if ((rc = ensure_workspace(op, nstates, maxorder))) return rc;
-        RMB_CUDA(cudaMemsetAsync(op->d_ctrl, 0, sizeof(int) * 4, st));
+        RMB_CUDA(cudaMemsetAsync(op->W->d_ctrl, 0, sizeof(int) * 4, st));
         op->defer_error = true;
     }
     for (int i = 0; i < nsteps; ++i) {
@@ -1516,6 +1583,7 @@ int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, i
         if (skip && !h0phase_dev) skip = 0;            // without H0 the reference always runs the Krylov part
         rc = propagate_device(op, (cplx*)psi_dev, nstates, ld, fac, tol, maxorder, (const cplx*)h0phase_dev, skip,
                               (i == nsteps - 1) ? orders_host : nullptr, st);
+        commit_spec(op);
         if (rc == RMB_ERR_MAXORDER) result = rc;
         else if (rc != RMB_OK) { op->defer_error = false; return rc; }
         if (nobs > 0 && (i % obs_every) == obs_every - 1) {
@@ -1528,9 +1596,9 @@ int32_t rmb_propagate_many(rmb_operator* op, double* psi_dev, int64_t nstates, i
     }
     if (fused) {
         op->defer_error = false;
-        k_publish<<<1, 32, 0, st>>>(op->d_ctrl, op->hd_ctrl, 1);
+        k_publish<<<1, 32, 0, st>>>(op->W->d_ctrl, op->W->hd_ctrl, 1);
         RMB_CUDA(cudaStreamSynchronize(st));
-        if (op->h_ctrl[0]) result = RMB_ERR_MAXORDER;
+        if (op->W->h_ctrl[0]) result = RMB_ERR_MAXORDER;
     }
     if (result == RMB_ERR_MAXORDER) {
         char buf[128];
@@ -1630,25 +1698,97 @@ int32_t rmb_propagate_step_host_obs(rmb_operator* op, const double* psi_in_host,
         op->pipe_orders_cap = nstates;
     }
     op->pipe_orders = op->d_pipe_orders;
-    for (int c = 0; c < nchunk; ++c) {
-        const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
-        RMB_CUDA(cudaStreamWaitEvent(st, op->pipe_events[2 * c], 0));
-        rc = propagate_device(op, op->d_stage + c0 * ld, b, ld, make_double2(fac_re, fac_im), tol, maxorder, ph,
-                              skip_krylov, nullptr, st);
-        if (rc == RMB_ERR_MAXORDER) result = rc;
-        else if (rc != RMB_OK) { op->pipe_orders = nullptr; return rc; }
-        for (int o = 0; o < nobs; ++o) {
-            rc = rmb_expectation(obs[o], (const double*)(op->d_stage + c0 * ld), b, ld,
-                                 (double*)(op->d_expv + (long long)o * nstates + c0), st);
-            if (rc != RMB_OK) return rc;
+    // Co-running chunks: chunk c runs on compute stream c % NWS with workspace c % NWS (the caller's stream is stream
+    // 0), its Lanczos loop enqueued speculatively (lanczos_begin) and finished (lanczos_finish) only when its workspace
+    // is needed again, so that up to NWS chunks fill the GPU together: a chunk alone is too small to do so and its
+    // per-iteration scalar tails leave gaps.  Falls back to one chunk after the other for the single-launch fused
+    // step, for skipped steps and when a chunk does not fit one workspace.
+    const cplx fac = make_double2(fac_re, fac_im);
+    static const int nws_env = getenv("RMB_CORUN") ? std::max(1, std::min(RMB_NWS, atoi(getenv("RMB_CORUN")))) : RMB_NWS;
+    const bool fused_step = op->fused_ok && cs <= 65535 && cs * op->n * (long long)sizeof(cplx) * (maxorder + 2) <= (1LL << 30);
+    // (chunks that fill the GPU on their own -- 64 MB of state vector and more -- gain nothing from sharing it and would
+    // only delay the first download: measured on the H2S and OCS batches, tools/r02_m.sh)
+    const bool small_chunk = (double)cs * (double)op->np * 16.0 < 64e6 || getenv("RMB_CORUN") != nullptr;
+    bool corun = nws_env > 1 && nchunk > 1 && small_chunk && !skip_krylov && !fused_step && check_field(op) == RMB_OK &&
+                 maxorder >= 1 && maxorder <= MAX_ORDER_SMEM;
+    const int NW = corun ? std::min(nws_env, nchunk) : 1;
+    if (corun) {
+        for (int i = 0; i < NW && corun; ++i) {
+            op->W = &op->wsp[i];
+            for (int o = 0; o < nobs; ++o) obs[o]->W = &obs[o]->wsp[i];
+            if (i > 0 && !op->s_c[i]) RMB_CUDA(cudaStreamCreateWithFlags(&op->s_c[i], cudaStreamNonBlocking));
+            if (ensure_workspace(op, cs, maxorder) != RMB_OK || op->W->ws_states < cs) corun = false;
         }
-        RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c + 1], st));
-        mark(st);
+        op->W = &op->wsp[0];
+        for (int o = 0; o < nobs; ++o) obs[o]->W = &obs[o]->wsp[0];
+    }
+    auto finish_chunk = [&](int c) -> int {
+        // second half of chunk c: finish its Lanczos loop, observables, download
+        const int wi = corun ? c % NW : 0;
+        const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
+        cudaStream_t sc = wi == 0 ? st : op->s_c[wi];
+        int rc2;
+        if (corun) {
+            op->W = &op->wsp[wi];
+            bool hit = false;
+            rc2 = lanczos_finish(op, nullptr, &hit);
+            op->W = &op->wsp[0];
+            if (rc2) return rc2;
+            if (hit) result = RMB_ERR_MAXORDER;
+        }
+        for (int o = 0; o < nobs; ++o) {
+            obs[o]->W = &obs[o]->wsp[wi];
+            rc2 = rmb_expectation(obs[o], (const double*)(op->d_stage + c0 * ld), b, ld,
+                                  (double*)(op->d_expv + (long long)o * nstates + c0), sc);
+            obs[o]->W = &obs[o]->wsp[0];
+            if (rc2 != RMB_OK) return rc2;
+        }
+        RMB_CUDA(cudaEventRecord(op->pipe_events[2 * c + 1], sc));
+        mark(sc);
         RMB_CUDA(cudaStreamWaitEvent(op->s_out, op->pipe_events[2 * c + 1], 0));
         RMB_CUDA(cudaMemcpyAsync((cplx*)psi_out_host + c0 * ld, op->d_stage + c0 * ld, sizeof(cplx) * b * ld,
                                  cudaMemcpyDeviceToHost, op->s_out));
         mark(op->s_out);
+        return RMB_OK;
+    };
+    if (corun) {
+        // field-dependent tables of the matvec kernels and everything else already enqueued on the caller's stream must
+        // be visible to the other compute streams
+        if ((rc = matvec_prep(op, st, op->lin_ok && cs >= 4 * op->lin_T))) return rc;
+        for (int o = 0; o < nobs; ++o)
+            if ((rc = matvec_prep(obs[o], st, obs[o]->lin_ok && cs >= 4 * obs[o]->lin_T))) return rc;
+        RMB_CUDA(cudaEventRecord(op->pipe_events[2 * nchunk], st));
+        for (int i = 1; i < NW; ++i) RMB_CUDA(cudaStreamWaitEvent(op->s_c[i], op->pipe_events[2 * nchunk], 0));
     }
+    for (int c = 0; c < nchunk; ++c) {
+        const long long c0 = c * cs, b = std::min(cs, (long long)nstates - c0);
+        if (!corun) {
+            RMB_CUDA(cudaStreamWaitEvent(st, op->pipe_events[2 * c], 0));
+            rc = propagate_device(op, op->d_stage + c0 * ld, b, ld, fac, tol, maxorder, ph, skip_krylov, nullptr, st);
+            if (rc == RMB_ERR_MAXORDER) result = rc;
+            else if (rc != RMB_OK) { op->pipe_orders = nullptr; return rc; }
+            if ((rc = finish_chunk(c))) { op->pipe_orders = nullptr; return rc; }
+            continue;
+        }
+        if (c >= NW && (rc = finish_chunk(c - NW))) { op->pipe_orders = nullptr; op->W = &op->wsp[0]; return rc; }
+        const int wi = c % NW;
+        cudaStream_t sc = wi == 0 ? st : op->s_c[wi];
+        RMB_CUDA(cudaStreamWaitEvent(sc, op->pipe_events[2 * c], 0));
+        op->W = &op->wsp[wi];
+        rc = lanczos_begin(op, op->d_stage + c0 * ld, b, ld, fac, tol, maxorder, ph, sc);
+        op->W = &op->wsp[0];
+        if (rc) { op->pipe_orders = nullptr; return rc; }
+    }
+    if (corun) {
+        for (int c = std::max(0, nchunk - NW); c < nchunk; ++c)
+            if ((rc = finish_chunk(c))) { op->pipe_orders = nullptr; op->W = &op->wsp[0]; return rc; }
+        // the caller's stream continues only after the other compute streams are done
+        for (int i = 1; i < NW; ++i) {
+            RMB_CUDA(cudaEventRecord(op->pipe_events[2 * nchunk], op->s_c[i]));
+            RMB_CUDA(cudaStreamWaitEvent(st, op->pipe_events[2 * nchunk], 0));
+        }
+    }
+    commit_spec(op);
     op->pipe_orders = nullptr;
     // small results last, on the download stream (behind the last chunk: nothing on the compute stream ever waits for
     // the D2H copy engine)
@@ -1702,12 +1842,12 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
     const long long n = op->n, np = op->np;
     if (nstates == 0) return RMB_OK;
     if ((rc = scratch_for(op, nstates, st))) return rc;
-    const long long bc = op->ws_states;
-    const int nch = op->nchunk;
+    const long long bc = op->W->ws_states;
+    const int nch = op->W->nchunk;
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, (long long)nstates - s0);
         const dim3 ugrid((unsigned)nchunks(n), (unsigned)b);
-        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->slabs[0], np, n,
+        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->W->slabs[0], np, n,
                                                     op->d_pmap);
         op->n_launches++;
         const bool lin = op->lin_ok && b >= 4 * op->lin_T;      // same routing as lanczos_batch
@@ -1715,17 +1855,17 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
             // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
             // the product vector itself is never written
             MvEpilogue ep;
-            ep.pdot = op->d_pdot;
+            ep.pdot = op->W->d_pdot;
             ep.use_lin = lin;
             ep.npart = ep.use_lin ? op->lin_npart : dot_parts(op);
-            if ((rc = launch_matvec(op, op->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
-            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
+            if ((rc = launch_matvec(op, op->W->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
+            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->W->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;
         } else {
-            if ((rc = launch_matvec(op, op->slabs[0], op->d_w, b, np, np, nullptr, st))) return rc;
-            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(op->slabs[0], np, op->d_w, np, np,
-                                                                             op->d_pdot, nch);
-            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->d_pdot, nch, (cplx*)expval_dev + s0, 1.0);
+            if ((rc = launch_matvec(op, op->W->slabs[0], op->W->d_w, b, np, np, nullptr, st))) return rc;
+            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(op->W->slabs[0], np, op->W->d_w, np, np,
+                                                                             op->W->d_pdot, nch);
+            k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->W->d_pdot, nch, (cplx*)expval_dev + s0, 1.0);
             op->n_launches += 2;
         }
         op->n_state_matvecs += b;

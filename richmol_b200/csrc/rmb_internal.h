@@ -61,6 +61,56 @@ int cuda_fail(cudaError_t e, const char* what);
 
 }  // namespace rmb
 
+namespace rmb {
+constexpr int RMB_NWS = 3;
+// parameters of a Lanczos loop that has been started (lanczos_begin) and not yet finished (lanczos_finish)
+struct LzRun {
+    cplx* psi = nullptr;
+    long long B = 0, ld = 0;
+    cplx fac;
+    double tol = 0;
+    int maxorder = 0;
+    const cplx* ph = nullptr;
+    cudaStream_t st = nullptr;
+    int nsl_p = 1, cps_p = 1, nsl_u = 1, cps_u = 1;   // sliced grids of the vector kernels
+    bool lin = false, fused = false;
+    int npart = 0;
+    int k_last = -1;                 // last iteration enqueued
+    bool open = false;
+};
+// ---- Krylov workspace (lazily sized): everything a Lanczos loop over one batch of states writes ----
+struct Workspace {
+    long long ws_states = 0;         // capacity in states of each slab
+    std::vector<rmb::cplx*> slabs;   // V_0, V_1, ... each ws_states * n
+    rmb::cplx* d_w = nullptr;        // H V_k
+    rmb::cplx** d_slab_ptrs = nullptr;   // device copy of slab pointers
+    int slab_ptrs_cap = 0;
+    int slab_ptrs_uploaded = 0;
+    // per-state small arrays (capacity ws_states, order capacity ws_maxorder)
+    int ws_maxorder = 0;
+    rmb::cplx* d_alpha = nullptr;    // [S][maxorder]
+    double* d_beta = nullptr;        // [S][maxorder+1]
+    rmb::cplx* d_ccur = nullptr;     // [S][maxorder]
+    rmb::cplx* d_dc = nullptr;       // [S][maxorder] (c^k - c^{k-1}) * rinv
+    rmb::cplx* d_ceff = nullptr;     // [S][maxorder] c^k * rinv
+    double* d_rinv = nullptr;        // [S][maxorder+1] 1/beta_k (1 for k = 0 and after a fallback)
+    std::vector<cudaEvent_t> it_events;
+    int* d_active = nullptr;         // [S]
+    int* d_order = nullptr;          // [S]
+    rmb::cplx* d_pdot = nullptr;     // [S][nchunk]
+    double* d_pnrm = nullptr;        // [S][nchunk]
+    double* d_pconv = nullptr;       // [S][nchunk]
+    double* d_pg0 = nullptr;         // [S][nchunk]  partial <V_0,V_0> (k_recur_gram, k = 0)
+    double* d_gdiag = nullptr;       // [S][maxorder+1]  <V_i,V_i> (diagonal of the Gram matrix of the Krylov vectors)
+    unsigned* d_ticket = nullptr;    // [S]  arrival counter of k_recur_gram's CTAs per state
+    int* d_ctrl = nullptr;           // per iteration k: [4k] states still active, [4k+1] maxorder flag
+    int* h_ctrl = nullptr;           // pinned + mapped mirror, written by k_publish
+    int* hd_ctrl = nullptr;          // its device address
+    int nchunk = 0;
+    LzRun run;                       // the Lanczos loop in flight on this workspace
+};
+}  // namespace rmb
+
 struct rmb_operator {
     int device = 0;
     int num_sms = 148;
@@ -153,36 +203,16 @@ struct rmb_operator {
 
     // ---- Krylov workspace (lazily sized) ----
     long long ws_budget = 0;         // bytes; 0 = auto
-    long long ws_states = 0;         // capacity in states of each slab
-    std::vector<rmb::cplx*> slabs;   // V_0, V_1, ... each ws_states * n
-    rmb::cplx* d_w = nullptr;        // H V_k
-    rmb::cplx** d_slab_ptrs = nullptr;   // device copy of slab pointers
-    int slab_ptrs_cap = 0;
-    int slab_ptrs_uploaded = 0;
-    // per-state small arrays (capacity ws_states, order capacity ws_maxorder)
-    int ws_maxorder = 0;
-    rmb::cplx* d_alpha = nullptr;    // [S][maxorder]
-    double* d_beta = nullptr;        // [S][maxorder+1]
-    rmb::cplx* d_ccur = nullptr;     // [S][maxorder]
-    rmb::cplx* d_dc = nullptr;       // [S][maxorder] (c^k - c^{k-1}) * rinv
-    rmb::cplx* d_ceff = nullptr;     // [S][maxorder] c^k * rinv
-    double* d_rinv = nullptr;        // [S][maxorder+1] 1/beta_k (1 for k = 0 and after a fallback)
-    std::vector<cudaEvent_t> it_events;
-    int* d_active = nullptr;         // [S]
-    int* d_order = nullptr;          // [S]
-    rmb::cplx* d_pdot = nullptr;     // [S][nchunk]
-    double* d_pnrm = nullptr;        // [S][nchunk]
-    double* d_pconv = nullptr;       // [S][nchunk]
-    double* d_pg0 = nullptr;         // [S][nchunk]  partial <V_0,V_0> (k_recur_gram, k = 0)
-    double* d_gdiag = nullptr;       // [S][maxorder+1]  <V_i,V_i> (diagonal of the Gram matrix of the Krylov vectors)
-    unsigned* d_ticket = nullptr;    // [S]  arrival counter of k_recur_gram's CTAs per state
-    int* d_ctrl = nullptr;           // per iteration k: [4k] states still active, [4k+1] maxorder flag
-    int* h_ctrl = nullptr;           // pinned + mapped mirror, written by k_publish
-    int* hd_ctrl = nullptr;          // its device address
+    // one workspace per compute stream of the host-buffer pipeline (chunks co-run on alternating streams); `W` is
+    // the one the next enqueued work uses -- every other entry point runs on wsp[0]
+    rmb::Workspace wsp[rmb::RMB_NWS];
+    rmb::Workspace* W = &wsp[0];
+    int spec_guess = 2;              // iteration at which the previous call ran out of active states (speculative enqueue)
+    int spec_seen = 0;               // maximum over the batches of the call in flight
+    cudaStream_t s_c[rmb::RMB_NWS] = {nullptr, nullptr, nullptr};   // compute streams 1.. of the pipeline ([0] = caller's)
     int* d_pipe_orders = nullptr;    // host-buffer pipeline: Lanczos orders of all chunks (one download at the end)
     int* pipe_orders = nullptr;      // write cursor into d_pipe_orders while a pipeline call is in flight, else nullptr
     long long pipe_orders_cap = 0;
-    int nchunk = 0;
     // host staging for the *_host entry point
     rmb::cplx* d_stage = nullptr;
     long long stage_elems = 0;
