@@ -1431,6 +1431,19 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
         fa.ld = ld;
         fa.order = op->W->d_order;
         fa.ctrl = op->W->d_ctrl;
+        fa.lin_blk = nullptr;
+        fa.lin_flat = nullptr;
+        fa.lin_val = nullptr;
+        static const bool gram_f = !(getenv("RMB_GRAM") && atoi(getenv("RMB_GRAM")) == 0);
+        static const bool fused_lin = !(getenv("RMB_FUSED_LIN") && atoi(getenv("RMB_FUSED_LIN")) == 0);
+        fa.gram_kmax = gram_f ? RMB_GRAM_KMAX : 0;
+        if (op->lin_ok && fused_lin) {
+            // merged entry lists of the sliding-window kernel (rebuilt after a field update)
+            if ((rc = matvec_prep(op, st, true))) return rc;
+            fa.lin_blk = (const LinBlk*)op->d_lin_blk;
+            fa.lin_flat = (const LinEnt*)op->d_lin_flat;
+            fa.lin_val = op->d_lin_val;
+        }
         // the history slabs are indexed [slab][state * n + i] with the leading dimension of this batch
         k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS,
                           (size_t)3 * n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd), st>>>(fa, nstates);

@@ -13,6 +13,7 @@
 #pragma once
 #include "rmb_kernels.cuh"
 #include "rmb_matvec.cuh"
+#include "rmb_matvec_lin.cuh"
 
 namespace rmb {
 
@@ -39,6 +40,12 @@ struct FusedArgs {
     long long ld;
     int* order;                  // [nstates]
     int* ctrl;                   // [1] maxorder flag
+    // merged entry lists of the sliding-window matvec (k_lin_entries), when the operator has them: per bra block the
+    // surviving (ket block, diagonal) pairs with K * MF folded into one value per row
+    const LinBlk* lin_blk;       // null: walk the products (fused_matvec)
+    const LinEnt* lin_flat;      // [nblocks][ML_FLAT]; record 0 = header (count), LinEnt::pad = ket block
+    const cplx* lin_val;
+    int gram_kmax;               // iterations whose convergence metric uses the Gram diagonal (0: always explicit)
 };
 
 template <int NT>
@@ -103,67 +110,146 @@ __device__ __forceinline__ void fused_matvec(const FusedArgs& a, const FusedProd
     }
 }
 
+constexpr int FUSED_ROWS = 9;      // rows per thread: n <= 210 KB / 48 B = 4375 <= 9 * 512
+
+// block sum of two values at once (one pair of barriers); same value in every thread, fixed order
+__device__ __forceinline__ double2 block_sum2_all(double x, double y, double2* sm /* FUSED_THREADS / 32 */) {
+    x = warp_sum(x);
+    y = warp_sum(y);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[wid] = make_double2(x, y);
+    __syncthreads();
+    double2 r = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < FUSED_THREADS / 32; ++i) { r.x += sm[i].x; r.y += sm[i].y; }
+    return r;
+}
+
+// Second generation of the single-launch step.  Against the first one: the matvec walks the MERGED entry lists of
+// k_lin_entries (one value per (entry, row) with K folded in, all loads of a row independent: one L2 latency per row
+// instead of one per product), row -> block lookups are hoisted out of the iteration loop, alpha rides on the matvec
+// pass, the convergence metric uses the Gram diagonal (as the batched path: rmb_lanczos.cuh) for the first
+// `gram_kmax` iterations, so no pass over the Krylov history, and warp 0 evaluates the small exponential while the
+// other warps already normalise V_{k+1}.  Five block reductions and three passes per iteration become two and three.
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 k_lanczos_fused(const FusedArgs a, long long nstates) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* vk = reinterpret_cast<cplx*>(smem_raw);       // V_k
     cplx* vkm1 = vk + a.n;                              // V_{k-1}
     cplx* w = vkm1 + a.n;                               // H V_k, then W_k
-    FusedProd* sp = reinterpret_cast<FusedProd*>(w + a.n);   // [nprod]
+    FusedProd* sp = reinterpret_cast<FusedProd*>(w + a.n);   // [nprod] (only without entry lists)
+    __shared__ double2 red2[FUSED_THREADS / 32];
     __shared__ double red[FUSED_THREADS / 32];
     __shared__ double2 s_alpha[MAX_ORDER_SMEM];
-    __shared__ double s_beta[MAX_ORDER_SMEM + 1];
+    __shared__ double s_beta[MAX_ORDER_SMEM + 1], s_g[MAX_ORDER_SMEM + 1];
     __shared__ double2 s_c[MAX_ORDER_SMEM], s_dc[MAX_ORDER_SMEM];
     __shared__ double2 s_y[MAX_ORDER_SMEM], s_t1[MAX_ORDER_SMEM], s_t2[MAX_ORDER_SMEM];
+    __shared__ double s_conv;
     const long long s = blockIdx.x;
     cplx* psi = a.psi + s * a.ld;
     const long long n = a.n;
+    const bool lin = a.lin_blk != nullptr;
 
-    // V_0 = psi * ph (not normalised, tdse.py:443 / 375)
+    // rows of this thread: block and position inside it (fixed for the whole step)
+    int rb[FUSED_ROWS], rm[FUSED_ROWS];
+#pragma unroll
+    for (int r = 0; r < FUSED_ROWS; ++r) {
+        const long long i = threadIdx.x + (long long)r * FUSED_THREADS;
+        rb[r] = 0;
+        rm[r] = 0;
+        if (i < n) {
+            rb[r] = a.row_blk[i];
+            rm[r] = (int)(i - a.blk_off[rb[r]]);
+        }
+    }
+    // V_0 = psi * ph (not normalised, tdse.py:443 / 375); <V_0, V_0> for the Gram diagonal
+    double g0 = 0.0;
     for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
         cplx v = psi[i];
         if (a.ph) v = cmul(v, a.ph[i]);
         vk[i] = v;
         a.slabs[0][s * n + i] = v;
+        g0 += cabs2(v);
     }
-    for (int p = threadIdx.x; p < a.nprod; p += FUSED_THREADS) {
-        const ProdD pr = a.prods[p];
-        FusedProd f;
-        f.ket_off = (int)pr.ket_off;
-        f.ent_off = (int)pr.ent_off;
-        f.nnz = __popc(a.tab_mask[pr.tab]);
-        f.pad = 0;
-        if (a.k_complex) {
-            const cplx kv = reinterpret_cast<const cplx*>(a.kpool)[pr.koff];
-            f.kre = kv.x;
-            f.kim = kv.y;
-        } else {
-            f.kre = a.kpool[pr.koff];
-            f.kim = 0.0;
+    if (!lin)
+        for (int p = threadIdx.x; p < a.nprod; p += FUSED_THREADS) {
+            const ProdD pr = a.prods[p];
+            FusedProd f;
+            f.ket_off = (int)pr.ket_off;
+            f.ent_off = (int)pr.ent_off;
+            f.nnz = __popc(a.tab_mask[pr.tab]);
+            f.pad = 0;
+            if (a.k_complex) {
+                const cplx kv = reinterpret_cast<const cplx*>(a.kpool)[pr.koff];
+                f.kre = kv.x;
+                f.kim = kv.y;
+            } else {
+                f.kre = a.kpool[pr.koff];
+                f.kim = 0.0;
+            }
+            sp[p] = f;
         }
-        sp[p] = f;
-    }
-    if (threadIdx.x == 0) { s_c[0] = make_double2(1.0, 0.0); s_beta[0] = 0.0; }
+    g0 = block_sum_all<FUSED_THREADS>(g0, red);
+    if (threadIdx.x == 0) { s_c[0] = make_double2(1.0, 0.0); s_beta[0] = 0.0; s_g[0] = g0; }
     __syncthreads();
 
     int k = 0, last = 0;
     bool hit_max = (a.maxorder <= 1);
     for (;; ++k) {
-        // w = H V_k ; alpha_k = vdot(w, V_k)
-        fused_matvec(a, sp, vk, w);
-        __syncthreads();
+        // ---- w = H V_k and alpha_k = vdot(w, V_k) in one pass
         double re = 0, im = 0;
-        for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
-            const cplx x = w[i], y = vk[i];
-            re += x.x * y.x + x.y * y.y;
-            im += x.x * y.y - x.y * y.x;
+        if (lin) {
+#pragma unroll
+            for (int r = 0; r < FUSED_ROWS; ++r) {
+                const long long i = threadIdx.x + (long long)r * FUSED_THREADS;
+                if (i < n) {
+                    const int b = rb[r], m = rm[r];
+                    const LinBlk bt = a.lin_blk[b];
+                    const LinEnt* fl = a.lin_flat + (size_t)b * ML_FLAT;
+                    const int L = (int)fl[0].xbyte;
+                    const cplx* ev = a.lin_val + bt.val_off + m;
+                    cplx acc = make_double2(0.0, 0.0);
+                    for (int j0 = 0; j0 < L; j0 += 4) {                 // four independent (entry, ket) load pairs per trip
+                        cplx e[4], v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            e[u] = v[u] = make_double2(0.0, 0.0);
+                            if (j0 + u < L) {
+                                const LinEnt f = fl[1 + j0 + u];
+                                e[u] = ev[(long long)(j0 + u) * bt.dm];
+                                const int col = min(max(m + f.doff, 0), f.dm2 - 1);   // outside the ket block e is zero
+                                v[u] = vk[a.blk_off[f.pad] + col];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            acc.x = fma(e[u].x, v[u].x, acc.x);
+                            acc.y = fma(e[u].x, v[u].y, acc.y);
+                            acc.x = fma(-e[u].y, v[u].y, acc.x);
+                            acc.y = fma(e[u].y, v[u].x, acc.y);
+                        }
+                    }
+                    w[i] = acc;
+                    const cplx y = vk[i];
+                    re += acc.x * y.x + acc.y * y.y;
+                    im += acc.x * y.y - acc.y * y.x;
+                }
+            }
+        } else {
+            fused_matvec(a, sp, vk, w);
+            __syncthreads();
+            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                const cplx x = w[i], y = vk[i];
+                re += x.x * y.x + x.y * y.y;
+                im += x.x * y.y - x.y * y.x;
+            }
         }
-        re = block_sum_all<FUSED_THREADS>(re, red);
-        im = block_sum_all<FUSED_THREADS>(im, red);
-        const cplx alpha = make_double2(re, im);
+        const double2 al = block_sum2_all(re, im, red2);
+        const cplx alpha = make_double2(al.x, al.y);
         const double beta = s_beta[k];
         if (threadIdx.x == 0) s_alpha[k] = alpha;
-        // W_k = w - alpha V_k - beta V_{k-1}; norm
+        // ---- W_k = w - alpha V_k - beta V_{k-1}; norm
         double nr = 0;
         for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
             cplx r = csub(w[i], cmul(alpha, vk[i]));
@@ -173,46 +259,70 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         }
         nr = block_sum_all<FUSED_THREADS>(nr, red);
         const double beta_next = sqrt(nr);
-        if (threadIdx.x == 0) s_beta[k + 1] = beta_next;
+        if (threadIdx.x == 0) {
+            s_beta[k + 1] = beta_next;
+            s_g[k + 1] = (beta_next != 0.0) ? nr / (beta_next * beta_next) : 1.0;      // <V_{k+1}, V_{k+1}>
+        }
         __syncthreads();
+        const bool use_gram = k < a.gram_kmax;
         bool done = false;
         if (k > 0) {
-            // c^k = expm(fac T_k) e_0 ; conv = sum |sum_i (c^k_i - c^{k-1}_i) V_i|^2
+            // c^k = expm(fac T_k) e_0 ; conv = sum |sum_i (c^k_i - c^{k-1}_i) V_i|^2 (tdse.py:474-476)
             if (threadIdx.x < 32) {
                 warp_expm_col0(k + 1, s_alpha, s_beta, a.fac, s_y, s_t1, s_t2);
+                double cv = 0.0;
                 for (int i = threadIdx.x; i <= k; i += 32) {
                     const cplx prev = (i < k) ? s_c[i] : make_double2(0.0, 0.0);
-                    s_dc[i] = csub(s_y[i], prev);
+                    const cplx d = csub(s_y[i], prev);
+                    s_dc[i] = d;
                     s_c[i] = s_y[i];
+                    cv += cabs2(d) * s_g[i];
                 }
+                cv = warp_sum(cv);
+                if (threadIdx.x == 0) s_conv = cv;                  // Gram-diagonal form of the metric
             }
-            __syncthreads();
-            double cv = 0;
+            if (!use_gram) {
+                // explicit evaluation over the Krylov history (many vectors: orthogonality is no longer a given)
+                __syncthreads();
+                double cv = 0;
+                for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
+                    cplx d = make_double2(0.0, 0.0);
+                    for (int j = 0; j + 2 <= k; ++j) cfma(d, s_dc[j], a.slabs[j][s * n + i]);
+                    cfma(d, s_dc[k - 1], vkm1[i]);
+                    cfma(d, s_dc[k], vk[i]);
+                    cv += cabs2(d);
+                }
+                cv = block_sum_all<FUSED_THREADS>(cv, red);
+                if (threadIdx.x == 0) s_conv = cv;
+            }
+        }
+        // ---- history: V_{k+1} = W_k / beta_{k+1} (tdse.py:455-456).  No barrier since the exponential started: the other
+        //      warps write the slab while warp 0 is still busy with it.  Written even if this turns out to be the last
+        //      iteration (nobody reads it then).
+        const bool fallback = beta_next == 0.0;
+        if (!fallback)
             for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
-                cplx d = make_double2(0.0, 0.0);
-                for (int j = 0; j + 2 <= k; ++j) cfma(d, s_dc[j], a.slabs[j][s * n + i]);
-                cfma(d, s_dc[k - 1], vkm1[i]);
-                cfma(d, s_dc[k], vk[i]);
-                cv += cabs2(d);
+                const cplx r = w[i];
+                a.slabs[k + 1][s * n + i] = make_double2(r.x / beta_next, r.y / beta_next);
             }
-            cv = block_sum_all<FUSED_THREADS>(cv, red);
+        __syncthreads();
+        if (k > 0) {
             last = k;
             if (k == a.maxorder - 1) { hit_max = true; done = true; }
-            else if (!(cv > a.tol)) done = true;
+            else if (!(s_conv > a.tol)) done = true;
         } else if (a.maxorder <= 1) {
             done = true;
         }
         if (done) break;
-        // V_{k+1} = W_k / beta_{k+1}, or the Gram-Schmidt fallback when beta_{k+1} == 0 (tdse.py:455-465)
-        if (beta_next != 0.0) {
+        // rotate: V_{k-1} <- V_k, V_k <- V_{k+1}
+        if (!fallback) {
             for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
                 const cplx r = w[i];
                 vkm1[i] = vk[i];
-                const cplx v = make_double2(r.x / beta_next, r.y / beta_next);
-                vk[i] = v;
-                a.slabs[k + 1][s * n + i] = v;
+                vk[i] = make_double2(r.x / beta_next, r.y / beta_next);
             }
         } else {
+            // zero-beta fallback (tdse.py:459-465): Gram-Schmidt of the all-ones vector against V_0..V_k
             for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
                 vkm1[i] = vk[i];
                 w[i] = make_double2(1.0, 0.0);

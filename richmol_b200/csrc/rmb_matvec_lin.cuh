@@ -28,7 +28,7 @@ constexpr int ML_NBMAX = 4;                          // entry buffers: 2 .. 4, a
 // one (product, surviving diagonal) of a bra block: byte offset of the ket block's ring slot, diagonal offset
 // (col - row) and rows of the ket block.  Record 0 of every per-block list is a header: xbyte = number of
 // entries that follow.
-struct __align__(16) LinEnt { unsigned xbyte; int doff; int dm2; int pad; };
+struct __align__(16) LinEnt { unsigned xbyte; int doff; int dm2; int pad; };   // pad: ket block of the entry
 constexpr int ML_FLAT = ML_LMAX + 1;                 // LinEnt records per bra block (header + entries)
 
 // static per-block data, copied to shared memory at kernel start
@@ -139,9 +139,7 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
     __syncthreads();
     const int L = s_L, U = s_U;
     for (int u = threadIdx.x; u < U; u += blockDim.x) {
-        LinEnt e = s_le[u];
-        e.pad = 0;
-        out[1 + u] = e;
+        out[1 + u] = s_le[u];                  // LinEnt::pad = ket block (read by the single-launch step, rmb_fused.cuh)
     }
     double2* vout = val + val_off[b];
     for (int i = threadIdx.x; i < U * dm1; i += blockDim.x) {

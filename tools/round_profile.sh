@@ -1,33 +1,39 @@
 #!/bin/bash
-# One gpurun call that produces everything profiles/ needs for a round (about 4 GPU-minutes on one B200):
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/round_profile.sh rNN'
-# Outputs under gpurun_out/<tag>_*: GPU test log, bench lines of both workloads, launch lists (duration + DRAM bytes
-# per launch) and one `ncu --set full` capture of each matvec kernel.  Summaries: tools/ncu_summary.py.
+# One gpurun call that produces everything profiles/ needs for a round (about 10 GPU-minutes on one B200):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/round_profile.sh rNN'
+# Outputs under gpurun_out/<tag>_*: GPU test log, the default bench line (all workloads), launch lists (duration + DRAM
+# bytes per launch) of the three batched workloads and one `ncu --set full` capture of each matvec kernel and of the
+# Lanczos recurrence kernel.  Summaries: tools/ncu_summary.py.
 tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
-(time python -m pytest tests -m gpu -x -q) > $out/${tag}_tests.log 2>&1
+(time timeout 1500 python -m pytest tests -m gpu -x -q) > $out/${tag}_tests.log 2>&1
 tail -3 $out/${tag}_tests.log
-python bench.py > $out/${tag}_bench_h2o.json 2> $out/${tag}_bench_h2o.err
-python bench.py --workload ocs --steps 40 > $out/${tag}_bench_ocs.json 2> $out/${tag}_bench_ocs.err
+(time timeout 1800 python bench.py) > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+tail -3 $out/${tag}_bench.err
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-ncu --metrics $M --clock-control none -c 600 --csv --log-file $out/${tag}_launches_h2o.csv \
-    python bench.py --steps 8 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --metrics $M --clock-control none -c 400 --csv --log-file $out/${tag}_launches_ocs.csv \
-    python bench.py --workload ocs --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_matvec_tiled -s 2 -c 1 -o $out/${tag}_tiled \
-    python tools/matvec_probe.py h2o > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_matvec_lin -s 2 -c 1 -o $out/${tag}_lin \
-    python tools/matvec_probe.py ocs > /dev/null 2>&1
+for wl in h2s h2o ocs_batch; do
+  timeout 900 ncu --metrics $M --clock-control none -c 400 --csv --log-file $out/${tag}_launches_$wl.csv \
+      python bench.py --workload $wl --steps 4 --warmup 3 --no-cpu-baseline --no-parity --also none > /dev/null 2>&1
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_matvec_dmma -s 1 -c 1 -o $out/${tag}_dmma \
+    python tools/matvec_probe.py h2s 64 3 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_matvec_tiled -s 1 -c 1 -o $out/${tag}_tiled \
+    python tools/matvec_probe.py h2o 500 100 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_matvec_lin -s 1 -c 1 -o $out/${tag}_lin \
+    python tools/matvec_probe.py ocs_batch 8192 100 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:k_recur_gram -s 3 -c 1 -o $out/${tag}_recur \
+    python bench.py --workload h2s --steps 2 --warmup 3 --no-cpu-baseline --no-parity --also none > /dev/null 2>&1
 python - <<PY
 import json
-for wl in ("h2o", "ocs"):
-    try:
-        d = json.load(open("$out/${tag}_bench_%s.json" % wl))
-        r = d["roofline"]
-        print(wl, "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]),
-              "matvec us", round(r["avg_launch_us"], 1), r["bound"], "frac", round(r["frac"], 3), "clocks", d["clocks"])
-    except Exception as e:
-        print(wl, "bench line missing:", e)
+d=json.loads(open("$out/${tag}_bench.json").read().strip().splitlines()[-1])
+def brief(r):
+    rf=r["roofline"]
+    print(f"{r.get('name','HEAD'):10s} value {r['value']:.1f} ms/step {r['ms_per_step']:.3f} steps {r['steps']} e2e {r['e2e']['value']:.1f} | {rf['bound']} frac {rf['frac']:.3f} share {rf['share_of_step']:.2f} mv/ss {rf['matvecs_per_state_step']:.2f} mv_us {rf['avg_launch_us']:.1f} | parity {r['parity']['ok']} | launches {r['gpu_launches']} | cpu {r.get('cpu_baseline',{}).get('value')}")
+brief(d)
+for r in d["workloads"]:
+    if "error" in r: print(r); continue
+    brief(r)
+print(d.get("cpu_baseline"))
 PY
 ls -la $out | grep ${tag}_
