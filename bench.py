@@ -558,6 +558,15 @@ def measured_peaks():
     return _PEAKS
 
 
+def ncu_traffic(workload):
+    """DRAM bytes (read + write) of one full-batch matvec launch from the committed ncu capture; None if there is none."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_matvec_traffic.json")))[workload]
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def op_info(op):
     """flops / operator bytes per state-matvec for the field currently applied (formulae of SURVEY.md 8d;
     only the M diagonals that survive the field contraction are counted, as in the reference's CSR), and the
@@ -652,7 +661,9 @@ def gpu_workload(w, args, headline, ctx):
     ops = [op] + ([cos2._device()] if cos2 is not None else [])
     cnt0 = [o.counters() for o in ops]
     ms_, n_ = C.c_double(), C.c_int64()
-    lib.rmb_matvec_timing(op.handle, 1, C.byref(ms_), C.byref(n_))     # enable + reset
+    ms_o, n_o = C.c_double(), C.c_int64()
+    for o in ops:
+        lib.rmb_matvec_timing(o.handle, 1, C.byref(ms_), C.byref(n_))  # enable + reset
     sampler = ClockSampler(ctx["local"])
     barrier()
     if rank == 0:
@@ -672,6 +683,8 @@ def gpu_workload(w, args, headline, ctx):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     lib.rmb_matvec_timing(op.handle, 0, C.byref(ms_), C.byref(n_))
+    for o in ops[1:]:
+        lib.rmb_matvec_timing(o.handle, 0, C.byref(ms_o), C.byref(n_o))   # the observable's matvec (<cos^2 theta>)
     cnt1 = [o.counters() for o in ops]
     launches = sum(b["launches"] - a["launches"] for a, b in zip(cnt0, cnt1))
     state_mv = cnt1[0]["state_matvecs"] - cnt0[0]["state_matvecs"]
@@ -721,14 +734,18 @@ def gpu_workload(w, args, headline, ctx):
     head = fp64 if compute_bound else hbm
     roofline = {
         "kernel": kernel, "bound": "tensor" if compute_bound else "hbm", "achieved": head["achieved"],
-        "peak": head["peak"], "unit": head["unit"], "frac": head["frac"], "traffic": None,
+        "peak": head["peak"], "unit": head["unit"], "frac": head["frac"], "traffic": ncu_traffic(w.name),
         "peak_source": head["peak_source"], "hbm": hbm, "fp64": fp64, "arithmetic_intensity": ai, "ridge": ridge,
         "flops_per_state_matvec": info["flops_per_state"], "bytes_per_state_matvec": 32.0 * N,
         "operator_bytes_per_launch": info["op_bytes"], "launches": int(mv_launches),
-        "avg_launch_us": mv_s / mv_launches * 1e6, "share_of_step": mv_s * 1e3 / ms,
+        "avg_launch_us": mv_s / mv_launches * 1e6,
+        # H.Psi launches of the Hamiltonian plus the one of the observable (same kernels, another operator handle)
+        "share_of_step": (mv_s * 1e3 + (0.0 if fused_step else ms_o.value)) / ms,
+        "share_of_step_hamiltonian_only": mv_s * 1e3 / ms,
         "matvecs_per_state_step": state_mv / max(1, nloc * steps),
-        "traffic_note": "dram bytes are not measured inside the timed run; ncu captures of the same kernels are under "
-                        "profiles/ (r02_*)",
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE full-batch launch of this kernel from the committed "
+                        "ncu --set full capture (profiles/r02_matvec_traffic.json, tools/round_profile.sh); not measured "
+                        "inside the timed run (a run under ncu is never a bench value); null where no capture exists",
     }
 
     del vecs
