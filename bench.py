@@ -753,6 +753,25 @@ def gpu_workload(w, args, headline, ctx):
     # ---- end to end through the public API with HOST buffers (numpy in, numpy out)
     e2e = e2e_run(w, m, args, new_tdse(), rows, ctx, counted, steps)
 
+    # ---- small ensembles: the same loop through the multi-step entry point (TDSE.propagate: one call, numpy in / out once,
+    #      observable every step) -- what a user of examples/ocs_alignment.py would call instead of 30 000 update() calls
+    multi = None
+    if fused_step and rank == 0:
+        try:
+            nst_m = 2000
+            tm = new_tdse()
+            terms = [(t["tensor"], None if t["static"] is not None else np.array([w.field(t["name"], i) for i in range(nst_m)]),
+                      t["thresh"]) for t in m["terms"]]
+            tm.propagate(terms, rows, H0=h0, expect=[cos2] if cos2 is not None else [])       # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tm.propagate(terms, rows, H0=h0, expect=[cos2] if cos2 is not None else [])
+            dtm = time.perf_counter() - t0
+            multi = {"value": nloc * nst_m / dtm, "unit": UNIT, "steps": nst_m,
+                     "note": "TDSE.propagate(terms, vecs, H0=, expect=[cos2]): all steps in one call, host arrays in and out"}
+        except Exception as e:
+            multi = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- parity self-check: the first steps again from the initial rows, a sample of rows against the oracle
     parity = parity_check(w, m, new_tdse(), rows, ctx) if rank == 0 and not args.no_parity else None
     torch.cuda.empty_cache()
@@ -771,6 +790,7 @@ def gpu_workload(w, args, headline, ctx):
                             "(SMALLER than the 126 MB L2: a latency-bound configuration, L2-resident by nature)"),
                    "model_build_s": round(t_build, 1)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": parity,
+        **({"multi_step_call": multi} if multi is not None else {}),
     }
 
 
@@ -922,6 +942,8 @@ def gpu_main(args, cpu_also=None):
     line["config"]["cpu_affinity"] = (f"rank 0 bound to {len(cpus)} cores of its GPU's NUMA node (NVML ideal affinity)"
                                       if cpus else "not bound")
     line["config"]["baseline_config"] = head["baseline_config"]
+    if "multi_step_call" in head:
+        line["multi_step_call"] = head["multi_step_call"]
     return line
 
 

@@ -715,9 +715,11 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 ebuf_elems = std::max(ebuf_elems, cap);
             }
             // T = 8 states per CTA (two groups of 4 per thread) with a ring of up to 2W+4 ket blocks (prefetch depth)
-            const char* ft = getenv("RMB_LIN_T");          // testing: force the 4-state tile
-            for (int pass = (ft && atoi(ft) == 4) ? 3 : 0; pass < 6 && !op->lin_ok; ++pass) {
-                const int T = pass < 3 ? 8 : 4;
+            // (RMB_LIN_T = 16 / 8 / 4 starts the search at that tile: testing and A/B runs)
+            const char* ft = getenv("RMB_LIN_T");
+            const int t_first = ft ? atoi(ft) : 8;
+            for (int pass = t_first >= 16 ? 0 : (t_first >= 8 ? 3 : 6); pass < 9 && !op->lin_ok; ++pass) {
+                const int T = pass < 3 ? 16 : (pass < 6 ? 8 : 4);
                 const int NS = 2 * W + 4 - pass % 3;
                 const size_t fixed = (size_t)NS * T * dmmax * 16 + (size_t)(2 * NS + ML_NBMAX + 1) * 8 +
                                      (size_t)d->nblocks * sizeof(LinBlk) + 128;
@@ -765,6 +767,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 RMB_CUDA(cudaMalloc((void**)&op->d_lin_val, (size_t)std::max<long long>(1, val_off[d->nblocks]) * sizeof(cplx)));
                 static bool g_lin_attr = false;
                 if (!g_lin_attr) {
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
@@ -997,6 +1000,9 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
         else if (op->lin_g1)
             k_matvec_lin<4, true><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
                                                                           ep.scale_stride, ep.pdot, ep.npart);
+        else if (T == 16)
+            k_matvec_lin<16><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                     ep.scale_stride, ep.pdot, ep.npart);
         else if (T == 8)
             k_matvec_lin<8><<<grid, ML_THREADS, op->lin_smem, st>>>(la, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
                                                                     ep.scale_stride, ep.pdot, ep.npart);
@@ -1860,9 +1866,15 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
     for (long long s0 = 0; s0 < nstates; s0 += bc) {
         const long long b = std::min(bc, (long long)nstates - s0);
         const dim3 ugrid((unsigned)nchunks(n), (unsigned)b);
-        k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>((const cplx*)psi_dev + s0 * ld, ld, nullptr, op->W->slabs[0], np, n,
-                                                    op->d_pmap);
-        op->n_launches++;
+        // user layout -> padded scratch; without padding (every dim_k odd, e.g. linear rotors) the kernels read psi in place
+        const cplx* X = (const cplx*)psi_dev + s0 * ld;
+        long long ldx = ld;
+        if (np != n) {
+            k_phase_init<<<ugrid, VEC_THREADS, 0, st>>>(X, ld, nullptr, op->W->slabs[0], np, n, op->d_pmap);
+            op->n_launches++;
+            X = op->W->slabs[0];
+            ldx = np;
+        }
         const bool lin = op->lin_ok && b >= 4 * op->lin_T;      // same routing as lanczos_batch
         if (lin || fused_dot(op)) {
             // <psi|O psi> = conj( sum conj(O psi) psi ): partial sums come out of the matvec epilogue and
@@ -1871,13 +1883,12 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
             ep.pdot = op->W->d_pdot;
             ep.use_lin = lin;
             ep.npart = ep.use_lin ? op->lin_npart : dot_parts(op);
-            if ((rc = launch_matvec(op, op->W->slabs[0], nullptr, b, np, np, nullptr, st, ep))) return rc;
+            if ((rc = launch_matvec(op, X, nullptr, b, ldx, np, nullptr, st, ep))) return rc;
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->W->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;
         } else {
-            if ((rc = launch_matvec(op, op->W->slabs[0], op->W->d_w, b, np, np, nullptr, st))) return rc;
-            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(op->W->slabs[0], np, op->W->d_w, np, np,
-                                                                             op->W->d_pdot, nch);
+            if ((rc = launch_matvec(op, X, op->W->d_w, b, ldx, np, nullptr, st))) return rc;
+            k_dot2<<<dim3((unsigned)nch, (unsigned)b), VEC_THREADS, 0, st>>>(X, ldx, op->W->d_w, np, np, op->W->d_pdot, nch);
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->W->d_pdot, nch, (cplx*)expval_dev + s0, 1.0);
             op->n_launches += 2;
         }
