@@ -14,6 +14,7 @@
 #include "rmb_fused.cuh"
 #include "rmb_matvec_dmma.cuh"
 #include "rmb_matvec_lin.cuh"
+#include "rmb_matvec_mw.cuh"
 
 namespace rmb {
 
@@ -71,6 +72,10 @@ void rmb_operator_destroy(rmb_operator* op) {
     cudaFree(op->d_lin_flat);
     cudaFree(op->d_lin_val);
     cudaFree(op->d_lin_val_off);
+    cudaFree(op->d_cshift);
+    cudaFree(op->d_cmap);
+    cudaFree(op->d_mw_counter);
+    for (auto& kv : op->mw_items_cache) cudaFree(kv.second.first);
     cudaFree(op->d_items2);
     cudaFree(op->d_itemsG);
     for (auto& kv : op->unitsG_cache) cudaFree(kv.second.first);
@@ -150,6 +155,16 @@ static void lin_update_bound(rmb_operator* op) {
         long long l = 0;
         for (int p = op->h_bra_begin[b]; p < op->h_bra_begin[b + 1]; ++p) l += alive[op->h_prods[p].tab];
         ebuf = std::max(ebuf, std::min<long long>(l, ML_LMAX) * op->h_blk_dm[b]);
+    }
+    // register-window kernel (rmb_matvec_mw.cuh): every diagonal that can survive the fields has |dm| <= 1
+    op->mw_cur = op->mw_static;
+    for (size_t p = 0; p < op->h_prods.size() && op->mw_cur; ++p) {
+        const int t = op->h_prods[p].tab;
+        const PartH& ph = op->parts[op->h_tab_part[t]];
+        const unsigned nz = ph.has_field ? (ph.all_dropped ? 0u : ph.nzmask) : 0xffffffffu;
+        for (int j = 0; j < op->h_prods[p].nd; ++j)
+            if ((op->h_diag_cart[op->h_diag_off[t] + j] & nz) && std::abs((int)op->h_prod_dm[op->h_prod_dm_off[p] + j]) > MW_DM)
+                op->mw_cur = false;
     }
     op->lin_ebuf_cur = (int)std::min<long long>(ebuf, op->lin_ebuf);
     const size_t per = (size_t)op->lin_ebuf_cur * 16 + ML_FLAT * sizeof(LinEnt);
@@ -776,6 +791,54 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 }
                 op->h_bra_begin = bra_begin;
                 op->h_blk_dm.assign(d->blk_dm, d->blk_dm + d->nblocks);
+                // ---- register-window kernel: blocks ordered by J with symmetric contiguous m ranges (rows grow by an even
+                //      number from block to block), block distance <= 2; per (product, diagonal) the m offset it couples
+                {
+                    // (opt-in, RMB_MW=1: correct -- the whole GPU suite passes with it -- but 2.3x slower than the ring kernel
+                    //  as it stands, 0.92 vs 0.39 ms on the OCS batch: latency-bound)
+                    bool ok = W <= MW_DB && getenv("RMB_MW") && atoi(getenv("RMB_MW")) == 1;
+                    std::vector<int> cshift(d->nblocks, 0);
+                    for (int b = 0; b + 1 < d->nblocks; ++b) {
+                        const int diff = d->blk_dm[b + 1] - d->blk_dm[b];
+                        if (diff < 0 || (diff & 1)) ok = false;
+                        cshift[b + 1] = cshift[b] + diff / 2;
+                    }
+                    op->h_prod_dm_off.assign(op->h_prods.size() + 1, 0);
+                    for (size_t p = 0; p < op->h_prods.size(); ++p) {
+                        const ProdD& q = op->h_prods[p];
+                        op->h_prod_dm_off[p] = (int)op->h_prod_dm.size();
+                        const int dm1p = op->h_prod_dm1[p];
+                        for (int j = 0; j < q.nd; ++j) {
+                            int doff = 0;
+                            bool found = false;
+                            for (int r = 0; r < dm1p && !found; ++r) {
+                                const int col = ent_col[q.ent_off + (long long)r * q.nd + j];
+                                if (col >= 0) { doff = col - r; found = true; }
+                            }
+                            const int dmq = doff - (cshift[h_prod_ket[p]] - cshift[h_prod_bra[p]]);
+                            op->h_prod_dm.push_back((signed char)std::max(-100, std::min(100, found ? dmq : 0)));
+                        }
+                    }
+                    op->h_prod_dm_off[op->h_prods.size()] = (int)op->h_prod_dm.size();
+                    op->mw_static = ok;
+                    op->mw_groups = (d->blk_dm[d->nblocks - 1] + 3) / 4;
+                    op->h_cshift = cshift;
+                    if ((rc = upload(&op->d_cshift, cshift.data(), cshift.size()))) return rc;
+                    RMB_CUDA(cudaMalloc((void**)&op->d_cmap, (size_t)d->nblocks * 16));
+                    RMB_CUDA(cudaMemset(op->d_cmap, 0xff, (size_t)d->nblocks * 16));
+                    RMB_CUDA(cudaMalloc((void**)&op->d_mw_counter, sizeof(int)));
+                    // first active block of every m-group
+                    op->h_mw_bfirst.assign(op->mw_groups, d->nblocks);
+                    for (int g = 0; g < op->mw_groups; ++g)
+                        for (int b = 0; b < d->nblocks; ++b) {
+                            bool any = false;
+                            for (int qq = 0; qq < 4; ++qq) {
+                                const int r = g * 4 + qq - (cshift[d->nblocks - 1] - cshift[b]);
+                                any = any || (r >= 0 && r < d->blk_dm[b] && g * 4 + qq < d->blk_dm[d->nblocks - 1]);
+                            }
+                            if (any) { op->h_mw_bfirst[g] = b; break; }
+                        }
+                }
                 lin_update_bound(op);
             }
         }
@@ -947,7 +1010,8 @@ static int matvec_prep(rmb_operator* op, cudaStream_t st, bool use_lin) {
             k_lin_entries<<<(unsigned)op->nblocks, 128, 0, st>>>(
                 op->nblocks, op->lin_NS, (unsigned)(op->lin_T * op->lin_dm_max * 16), op->d_blk_begin, op->d_blk_dm,
                 op->d_prod_ket, op->d_prods, op->d_tab_mask, (const MfEntry*)op->d_ent_cent, op->d_kpool,
-                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val);
+                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val, op->d_cshift,
+                op->mw_static ? op->d_cmap : nullptr);
             op->lin_flat_dirty = false;
             op->n_launches++;
         }
@@ -980,6 +1044,52 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             RMB_CUDA(cudaEventCreate(&ev.second));
         }
         RMB_CUDA(cudaEventRecord(ev.first, st));
+    }
+    if (ep.use_lin && op->lin_ok && op->mw_cur) {
+        // register-window kernel: items (m-group, 64-state super tile), longest walks first
+        auto hit = op->mw_items_cache.find(nstates);
+        if (hit == op->mw_items_cache.end()) {
+            std::vector<MwItem> items;
+            std::vector<int> order(op->mw_groups);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return op->h_mw_bfirst[x] < op->h_mw_bfirst[y]; });
+            for (int g : order)
+                for (long long t0 = 0; t0 < nstates; t0 += 8 * MW_WARPS) items.push_back({g, (int)t0, op->h_mw_bfirst[g], 0});
+            if (op->mw_items_cache.size() >= 16) {
+                RMB_CUDA(cudaStreamSynchronize(st));
+                for (auto& kv : op->mw_items_cache) cudaFree(kv.second.first);
+                op->mw_items_cache.clear();
+            }
+            void* dptr = nullptr;
+            RMB_CUDA(cudaMalloc(&dptr, sizeof(MwItem) * std::max<size_t>(1, items.size())));
+            RMB_CUDA(cudaMemcpyAsync(dptr, items.data(), sizeof(MwItem) * items.size(), cudaMemcpyHostToDevice, st));
+            RMB_CUDA(cudaStreamSynchronize(st));
+            hit = op->mw_items_cache.emplace(nstates, std::make_pair(dptr, (int)items.size())).first;
+        }
+        MwArgs ma;
+        ma.nblocks = op->nblocks;
+        ma.nitems = hit->second.second;
+        ma.dm_last = op->h_blk_dm[op->nblocks - 1];
+        ma.blk_off = op->d_blk_off;
+        ma.blk_dm = op->d_blk_dm;
+        ma.cshift = op->d_cshift;
+        ma.val_off = op->d_lin_val_off;
+        ma.cmap = op->d_cmap;
+        ma.val = op->d_lin_val;
+        ma.items = (const MwItem*)hit->second.first;
+        ma.counter = op->d_mw_counter;
+        RMB_CUDA(cudaMemsetAsync(op->d_mw_counter, 0, sizeof(int), st));
+        const unsigned grid = (unsigned)std::min<long long>(ma.nitems, 2LL * op->num_sms);
+        k_matvec_mw<<<grid, MW_THREADS, mw_smem_bytes(op->nblocks), st>>>(ma, X, Y, ldx, ldy, (int)nstates, active, ep.scale,
+                                                                          ep.scale_stride, ep.pdot, ep.npart);
+        op->n_launches++;
+        RMB_CUDA(cudaGetLastError());
+        if (op->time_matvec) {
+            RMB_CUDA(cudaEventRecord(ev.second, st));
+            op->mv_events.push_back(ev);
+        }
+        op->n_matvec_launches++;
+        return RMB_OK;
     }
     if (ep.use_lin && op->lin_ok) {
         LinArgs la;
@@ -1141,6 +1251,9 @@ static inline void commit_spec(rmb_operator* op) {
     op->spec_seen = 0;
 }
 
+// partial sums per state written by the linear-rotor matvec in use: m-groups (register-window kernel) or 32-row chunks
+static inline int lin_parts(const rmb_operator* op) { return op->mw_cur ? op->mw_groups : op->lin_npart; }
+
 // the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
 static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 + op->nitemsG > 0; }
 static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 + op->nitemsG : op->W->nchunk; }
@@ -1295,7 +1408,8 @@ static int lanczos_begin(rmb_operator* op, cplx* psi, long long B, long long ld,
     r.psi = psi; r.B = B; r.ld = ld; r.fac = fac; r.tol = tol; r.maxorder = maxorder; r.ph = ph; r.st = st;
     r.lin = op->lin_ok && B >= 4 * op->lin_T;      // large batches of linear rotors: sliding window
     r.fused = r.lin || fused_dot(op);
-    r.npart = r.lin ? op->lin_npart : dot_parts(op);
+    if (r.lin && op->lin_flat_dirty) lin_update_bound(op);       // decides which linear-rotor kernel runs (field dependent)
+    r.npart = r.lin ? lin_parts(op) : dot_parts(op);
     // sliced grids of the vector kernels: a CTA walks `cps` consecutive chunks of one state (~12 CTAs per SM in total)
     auto slices = [&](int nchunk_, int* nsl_, int* cps_) {
         const long long want = std::max<long long>(1, (12LL * op->num_sms + B - 1) / B);
@@ -1882,7 +1996,8 @@ int32_t rmb_expectation(rmb_operator* op, const double* psi_dev, int64_t nstates
             MvEpilogue ep;
             ep.pdot = op->W->d_pdot;
             ep.use_lin = lin;
-            ep.npart = ep.use_lin ? op->lin_npart : dot_parts(op);
+            if (lin && op->lin_flat_dirty) lin_update_bound(op);
+            ep.npart = ep.use_lin ? lin_parts(op) : dot_parts(op);
             if ((rc = launch_matvec(op, X, nullptr, b, ldx, np, nullptr, st, ep))) return rc;
             k_reduce_dot<<<(unsigned)b, 32, 0, st>>>(op->W->d_pdot, ep.npart, (cplx*)expval_dev + s0, -1.0);
             op->n_launches += 1;

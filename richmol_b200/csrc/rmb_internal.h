@@ -200,6 +200,16 @@ struct rmb_operator {
     std::vector<int> h_tab_part;     // [ntables] part owning the table
     std::vector<int> h_bra_begin;    // [nblocks + 1] products sorted by bra block
     std::vector<int> h_blk_dm;       // [nblocks]
+    // register-window kernel for linear rotors (rmb_matvec_mw.cuh)
+    bool mw_static = false;          // block structure allows it (symmetric contiguous m ranges, block distance <= 2)
+    bool mw_cur = false;             // ... and every diagonal that survives the current fields has |dm| <= 1
+    int mw_groups = 0;               // groups of 4 m values
+    std::vector<int> h_cshift, h_mw_bfirst, h_prod_dm_off;
+    std::vector<signed char> h_prod_dm;   // per (product, diagonal slot): m offset of the diagonal
+    int* d_cshift = nullptr;
+    unsigned char* d_cmap = nullptr; // [nblocks][16] (block distance, dm) -> merged entry (k_lin_entries)
+    int* d_mw_counter = nullptr;
+    std::map<long long, std::pair<void*, int>> mw_items_cache;   // batch size -> device item list
 
     // ---- Krylov workspace (lazily sized) ----
     long long ws_budget = 0;         // bytes; 0 = auto

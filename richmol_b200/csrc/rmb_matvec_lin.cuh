@@ -60,7 +60,8 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
               const int* __restrict__ blk_dm, const int* __restrict__ prod_ket, const ProdD* __restrict__ prods,
               const unsigned* __restrict__ tab_mask, const MfEntry* __restrict__ cent,
               const double* __restrict__ kpool, int k_complex, const long long* __restrict__ val_off,
-              LinEnt* __restrict__ flat, double2* __restrict__ val) {
+              LinEnt* __restrict__ flat, double2* __restrict__ val, const int* __restrict__ cshift,
+              unsigned char* __restrict__ cmap) {
     __shared__ long long s_ent[ML_LMAX];      // first compacted MF entry of the (product, diagonal) pair
     __shared__ double2 s_k[ML_LMAX];          // its 1 x 1 K factor
     __shared__ LinEnt s_le[ML_LMAX];          // its descriptor
@@ -134,6 +135,17 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
             out[0] = h;
             s_L = L;
             s_U = U;
+            if (cmap != nullptr) {
+                // (block distance, dm) -> merged entry, for the register-window kernel (rmb_matvec_mw.cuh): 5 x 3 slots,
+                // 0xff = absent; dm = doff - (row shift between the two blocks)
+                unsigned char* cm = cmap + (size_t)b * 16;
+                for (int c = 0; c < 16; ++c) cm[c] = 0xff;
+                for (int u = 0; u < U; ++u) {
+                    const int ket = s_le[u].pad;
+                    const int db = ket - b, dmq = s_le[u].doff - (cshift[ket] - cshift[b]);
+                    if (db >= -2 && db <= 2 && dmq >= -1 && dmq <= 1) cm[(db + 2) * 3 + (dmq + 1)] = (unsigned char)u;
+                }
+            }
         }
     }
     __syncthreads();
