@@ -156,8 +156,8 @@ static void lin_update_bound(rmb_operator* op) {
         for (int p = op->h_bra_begin[b]; p < op->h_bra_begin[b + 1]; ++p) l += alive[op->h_prods[p].tab];
         ebuf = std::max(ebuf, std::min<long long>(l, ML_LMAX) * op->h_blk_dm[b]);
     }
-    // register-window kernel (rmb_matvec_mw.cuh): every diagonal that can survive the fields has |dm| <= 1
-    op->mw_cur = op->mw_static;
+    // register-window kernels (k_matvec_linw, rmb_matvec_mw.cuh): every diagonal that can survive the fields has |dm| <= 1
+    op->mw_cur = op->sym_ok;
     for (size_t p = 0; p < op->h_prods.size() && op->mw_cur; ++p) {
         const int t = op->h_prods[p].tab;
         const PartH& ph = op->parts[op->h_tab_part[t]];
@@ -166,8 +166,25 @@ static void lin_update_bound(rmb_operator* op) {
             if ((op->h_diag_cart[op->h_diag_off[t] + j] & nz) && std::abs((int)op->h_prod_dm[op->h_prod_dm_off[p] + j]) > MW_DM)
                 op->mw_cur = false;
     }
+    op->lw_cur = op->mw_cur && op->lw_static;
+    op->mw_cur = op->mw_cur && op->mw_static;
     op->lin_ebuf_cur = (int)std::min<long long>(ebuf, op->lin_ebuf);
     const size_t per = (size_t)op->lin_ebuf_cur * 16 + ML_FLAT * sizeof(LinEnt);
+    {
+        // shared memory of k_matvec_linw: the same layout with a ring of 4-state tiles
+        // (deep rings: a block step of a 4-state tile is a few hundred cycles of work, a bulk copy takes a couple of
+        //  thousand to land, so the producers must run many blocks ahead)
+        const size_t slotb = (size_t)LW_T * op->lin_dm_max * 16;
+        const size_t misc = (size_t)(2 * 16 + 8 + 1) * 8 + (size_t)op->nblocks * sizeof(LinBlk) + 128;
+        int nb4 = (int)std::min<size_t>(8, (size_t)(0.55 * LIN_SMEM_MAX) / per);
+        nb4 = std::max(2, nb4);
+        size_t left = LIN_SMEM_MAX > misc + (size_t)nb4 * per ? LIN_SMEM_MAX - misc - (size_t)nb4 * per : 0;
+        int ns4 = (int)std::min<size_t>(16, left / slotb);
+        op->lw_NB = nb4;
+        op->lw_NS = ns4;
+        op->lw_smem = misc + (size_t)ns4 * slotb + (size_t)nb4 * per;
+        if (ns4 < op->lin_W + 3 || ns4 < 5 || op->lw_smem > LIN_SMEM_MAX) op->lw_cur = false;
+    }
     int nb = (int)((LIN_SMEM_MAX - op->lin_smem_fixed) / per);
     op->lin_NB = std::max(2, std::min(nb, ML_NBMAX));
     op->lin_smem = op->lin_smem_fixed + (size_t)op->lin_NB * per;
@@ -782,6 +799,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 RMB_CUDA(cudaMalloc((void**)&op->d_lin_val, (size_t)std::max<long long>(1, val_off[d->nblocks]) * sizeof(cplx)));
                 static bool g_lin_attr = false;
                 if (!g_lin_attr) {
+                    RMB_CUDA(cudaFuncSetAttribute(k_matvec_linw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
                     RMB_CUDA(cudaFuncSetAttribute(k_matvec_lin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIN_SMEM_MAX));
@@ -794,9 +812,11 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 // ---- register-window kernel: blocks ordered by J with symmetric contiguous m ranges (rows grow by an even
                 //      number from block to block), block distance <= 2; per (product, diagonal) the m offset it couples
                 {
-                    // (opt-in, RMB_MW=1: correct -- the whole GPU suite passes with it -- but 2.3x slower than the ring kernel
-                    //  as it stands, 0.92 vs 0.39 ms on the OCS batch: latency-bound)
-                    bool ok = W <= MW_DB && getenv("RMB_MW") && atoi(getenv("RMB_MW")) == 1;
+                    // Both register-window kernels are opt-in (RMB_MW=1: k_matvec_mw, RMB_LINW=1: k_matvec_linw).  They are correct
+                    // -- the whole GPU suite passes with either as the default -- but issue 3.4x the instructions of the ring
+                    // kernel for the same work and are slower as they stand: 0.92 / 1.24-1.34 ms against 0.39 ms on the OCS
+                    // batch (profiles/r02_linw_notes.md)
+                    bool ok = W <= MW_DB;
                     std::vector<int> cshift(d->nblocks, 0);
                     for (int b = 0; b + 1 < d->nblocks; ++b) {
                         const int diff = d->blk_dm[b + 1] - d->blk_dm[b];
@@ -820,7 +840,11 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         }
                     }
                     op->h_prod_dm_off[op->h_prods.size()] = (int)op->h_prod_dm.size();
-                    op->mw_static = ok;
+                    op->sym_ok = ok;
+                    op->mw_static = ok && getenv("RMB_MW") && atoi(getenv("RMB_MW")) == 1;
+                    op->lw_static = ok && d->blk_dm[d->nblocks - 1] <= 8 * LW_CWARPS && op->lin_NS >= W + 3 &&
+                                    getenv("RMB_LINW") && atoi(getenv("RMB_LINW")) == 1;
+                    op->lw_groups = (d->blk_dm[d->nblocks - 1] + 7) / 8;
                     op->mw_groups = (d->blk_dm[d->nblocks - 1] + 3) / 4;
                     op->h_cshift = cshift;
                     if ((rc = upload(&op->d_cshift, cshift.data(), cshift.size()))) return rc;
@@ -1010,8 +1034,8 @@ static int matvec_prep(rmb_operator* op, cudaStream_t st, bool use_lin) {
             k_lin_entries<<<(unsigned)op->nblocks, 128, 0, st>>>(
                 op->nblocks, op->lin_NS, (unsigned)(op->lin_T * op->lin_dm_max * 16), op->d_blk_begin, op->d_blk_dm,
                 op->d_prod_ket, op->d_prods, op->d_tab_mask, (const MfEntry*)op->d_ent_cent, op->d_kpool,
-                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val, op->d_cshift,
-                op->mw_static ? op->d_cmap : nullptr);
+                op->k_complex ? 1 : 0, op->d_lin_val_off, (LinEnt*)op->d_lin_flat, op->d_lin_val,
+                op->sym_ok ? op->d_cshift : nullptr, op->mw_static ? op->d_cmap : nullptr);
             op->lin_flat_dirty = false;
             op->n_launches++;
         }
@@ -1044,6 +1068,31 @@ static int launch_matvec(rmb_operator* op, const cplx* X, cplx* Y, long long nst
             RMB_CUDA(cudaEventCreate(&ev.second));
         }
         RMB_CUDA(cudaEventRecord(ev.first, st));
+    }
+    if (ep.use_lin && op->lin_ok && op->lw_cur) {
+        // ring + register window (k_matvec_linw): tiles of 4 states
+        LinArgs la;
+        la.nblocks = op->nblocks;
+        la.W = op->lin_W;
+        la.dms = op->lin_dm_max;
+        la.NS = op->lw_NS;
+        la.NB = op->lw_NB;
+        la.ebuf_elems = op->lin_ebuf_cur;
+        la.blk = (const LinBlk*)op->d_lin_blk;
+        la.flat = (const LinEnt*)op->d_lin_flat;
+        la.val = op->d_lin_val;
+        const unsigned grid = (unsigned)((nstates + LW_T - 1) / LW_T);
+        k_matvec_linw<<<grid, LW_THREADS, op->lw_smem, st>>>(la, op->h_blk_dm[op->nblocks - 1], op->lw_groups, X, Y, ldx, ldy,
+                                                             (int)nstates, active, ep.scale, ep.scale_stride, ep.pdot,
+                                                             ep.npart);
+        op->n_launches++;
+        RMB_CUDA(cudaGetLastError());
+        if (op->time_matvec) {
+            RMB_CUDA(cudaEventRecord(ev.second, st));
+            op->mv_events.push_back(ev);
+        }
+        op->n_matvec_launches++;
+        return RMB_OK;
     }
     if (ep.use_lin && op->lin_ok && op->mw_cur) {
         // register-window kernel: items (m-group, 64-state super tile), longest walks first
@@ -1252,7 +1301,9 @@ static inline void commit_spec(rmb_operator* op) {
 }
 
 // partial sums per state written by the linear-rotor matvec in use: m-groups (register-window kernel) or 32-row chunks
-static inline int lin_parts(const rmb_operator* op) { return op->mw_cur ? op->mw_groups : op->lin_npart; }
+static inline int lin_parts(const rmb_operator* op) {
+    return op->lw_cur ? op->lw_groups : (op->mw_cur ? op->mw_groups : op->lin_npart);
+}
 
 // the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
 static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 + op->nitemsG > 0; }

@@ -201,7 +201,11 @@ struct rmb_operator {
     std::vector<int> h_bra_begin;    // [nblocks + 1] products sorted by bra block
     std::vector<int> h_blk_dm;       // [nblocks]
     // register-window kernel for linear rotors (rmb_matvec_mw.cuh)
-    bool mw_static = false;          // block structure allows it (symmetric contiguous m ranges, block distance <= 2)
+    bool sym_ok = false;             // blocks ordered by J with symmetric contiguous m ranges, block distance <= 2
+    bool lw_static = false, lw_cur = false;   // ring + register window kernel (k_matvec_linw) usable / usable with the current fields
+    int lw_groups = 0, lw_NB = 2, lw_NS = 6;
+    size_t lw_smem = 0;
+    bool mw_static = false;          // standalone register-window kernel enabled (RMB_MW=1)
     bool mw_cur = false;             // ... and every diagonal that survives the current fields has |dm| <= 1
     int mw_groups = 0;               // groups of 4 m values
     std::vector<int> h_cshift, h_mw_bfirst, h_prod_dm_off;

@@ -29,7 +29,7 @@ constexpr int ML_NBMAX = 4;                          // entry buffers: 2 .. 4, a
 // (col - row) and rows of the ket block.  Record 0 of every per-block list is a header: xbyte = number of
 // entries that follow.
 struct __align__(16) LinEnt { unsigned xbyte; int doff; int dm2; int pad; };   // pad: ket block of the entry
-constexpr int ML_FLAT = ML_LMAX + 1;                 // LinEnt records per bra block (header + entries)
+constexpr int ML_FLAT = ML_LMAX + 2;                 // LinEnt records per bra block: header, entries, (block distance, dm) slot map
 
 // static per-block data, copied to shared memory at kernel start
 struct __align__(16) LinBlk {
@@ -135,16 +135,21 @@ k_lin_entries(int nblocks, int NS, unsigned slot_bytes, const int* __restrict__ 
             out[0] = h;
             s_L = L;
             s_U = U;
-            if (cmap != nullptr) {
-                // (block distance, dm) -> merged entry, for the register-window kernel (rmb_matvec_mw.cuh): 5 x 3 slots,
-                // 0xff = absent; dm = doff - (row shift between the two blocks)
-                unsigned char* cm = cmap + (size_t)b * 16;
-                for (int c = 0; c < 16; ++c) cm[c] = 0xff;
+            if (cshift != nullptr) {
+                // (block distance, dm) -> merged entry, for the register-window kernels (k_matvec_linw below,
+                // rmb_matvec_mw.cuh): 5 x 3 slots, 0xff = absent; dm = doff - (row shift between the two blocks).  Last
+                // record of the block's list (travels with the bulk copy of the entries) and, if given, the separate map.
+                unsigned char cmb[16];
+                for (int c = 0; c < 16; ++c) cmb[c] = 0xff;
                 for (int u = 0; u < U; ++u) {
                     const int ket = s_le[u].pad;
                     const int db = ket - b, dmq = s_le[u].doff - (cshift[ket] - cshift[b]);
-                    if (db >= -2 && db <= 2 && dmq >= -1 && dmq <= 1) cm[(db + 2) * 3 + (dmq + 1)] = (unsigned char)u;
+                    if (db >= -2 && db <= 2 && dmq >= -1 && dmq <= 1) cmb[(db + 2) * 3 + (dmq + 1)] = (unsigned char)u;
                 }
+                unsigned char* rec = reinterpret_cast<unsigned char*>(out + (ML_FLAT - 1));
+                for (int c = 0; c < 16; ++c) rec[c] = cmb[c];
+                if (cmap != nullptr)
+                    for (int c = 0; c < 16; ++c) cmap[(size_t)b * 16 + c] = cmb[c];
             }
         }
     }
@@ -360,6 +365,218 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
         if (lane == 0) mbar_arrive(&done[bs]);                // this warp is finished with bra block b
         if (++bs == NS) bs = 0;
         if (++es == NB) { es = 0; eph ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_matvec_linw: the same ring / producer protocol as k_matvec_lin for a tile of 4 states, but the compute warps keep
+// the ket elements in a REGISTER WINDOW.  Warp g owns the 8 row positions R = 8g .. 8g+7 (counted in the last, largest
+// block: blocks are ordered by J with symmetric m ranges, so the row of the same m in block b is
+// r_b = R - (dm_last - dm_b) / 2) of all 4 states for the whole walk: lane = (state, row position).  At bra block b it loads
+// the three elements x[b+2][m-1..m+1] that enter its 5 x 3 window from the ring (conflict-free LDS.128: 8 consecutive rows
+// of a state are 128 contiguous bytes and the state stride is odd) and the surviving entry values of its row (8 distinct
+// 16-byte words per load, broadcast to the 4 states): 3 + L loads of which L cost one wavefront, for 4 L DFMA -- 21
+// wavefronts per 36 warp-DFMA at L = 9 against 53 in k_matvec_lin, where every complex FMA fetches its ket element from
+// shared memory.  Requires |block distance| <= 2, |dm| <= 1 for every surviving diagonal (fields in a plane containing Z)
+// and dm_last <= 128; the host checks (rmb.cu: lin_update_bound).  Partial sums conj(y).x per (state, row group).
+constexpr int LW_CWARPS = 16;
+constexpr int LW_THREADS = (LW_CWARPS + 2) * 32;
+constexpr int LW_T = 4;
+
+__global__ void __launch_bounds__(LW_THREADS, 1)
+k_matvec_linw(const LinArgs a, int dm_last, int ngroups, const double2* __restrict__ X, double2* __restrict__ Y,
+              long long ldx, long long ldy, int nstates, const int* __restrict__ active,
+              const double* __restrict__ scale, int scale_stride, double2* __restrict__ pdot, int npart) {
+    constexpr int T = LW_T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NS = a.NS;
+    const int slot_elems = T * a.dms;                         // [state][row]
+    double2* ring = reinterpret_cast<double2*>(smem_raw);                     // [NS][T][dms]
+    double2* ebuf = ring + (size_t)NS * slot_elems;                           // [NB][ebuf_elems]
+    const int NB = a.NB;
+    LinEnt* flat = reinterpret_cast<LinEnt*>(ebuf + (size_t)NB * a.ebuf_elems);      // [NB][ML_FLAT]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(flat + NB * ML_FLAT);   // [NS]
+    unsigned long long* done = full + NS;                                     // [NS]
+    unsigned long long* efull = done + NS;                                    // [NB]
+    LinBlk* blk = reinterpret_cast<LinBlk*>(efull + NB + ((2 * NS + NB) & 1));        // [nblocks], 16-byte aligned
+    __shared__ long long s_sb[T];
+    __shared__ double s_sc[T];
+    __shared__ int s_nact;
+
+    const int s0 = blockIdx.x * T;
+    if (threadIdx.x < T) {
+        const int s = s0 + threadIdx.x;
+        const bool ok = s < nstates && (active == nullptr || active[s]);
+        s_sb[threadIdx.x] = ok ? (long long)s : -1;
+        s_sc[threadIdx.x] = (ok && scale != nullptr) ? scale[(long long)s * scale_stride] : 1.0;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], LW_CWARPS);
+        }
+        for (int i = 0; i < NB; ++i) mbar_init(&efull[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int b = threadIdx.x; b < a.nblocks; b += LW_THREADS) {
+        LinBlk t = a.blk[b];
+        t.L = (int)a.flat[(size_t)b * ML_FLAT].xbyte;
+        blk[b] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int i = 0; i < T; ++i) n += s_sb[i] >= 0 ? 1 : 0;
+        s_nact = n;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (nact == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp >= LW_CWARPS) {
+        // ================= producer warps (as in k_matvec_lin) =================
+        int ds = 0, dph = 0, dcnt = 0;
+        auto observe = [&](int need) {
+            while (dcnt <= need) {
+                mbar_wait(&done[ds], (unsigned)dph);
+                ++dcnt;
+                if (++ds == NS) { ds = 0; dph ^= 1; }
+            }
+        };
+        if (warp == LW_CWARPS) {
+            const long long sb = lane < T ? s_sb[lane] : -1;
+            const double2* xrow = X + (sb >= 0 ? sb : 0) * ldx;
+            double2* dst = ring + (size_t)lane * a.dms;
+            int xs = 0;
+            for (int j = 0; j < a.nblocks; ++j) {
+                observe(j - NS + a.W);
+                const LinBlk t = blk[j];
+                unsigned long long* bar = &full[xs];
+                if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)nact * (unsigned)t.dm * 16u);
+                __syncwarp();
+                if (sb >= 0) tma_load_1d(dst + (size_t)xs * slot_elems, xrow + t.off, (unsigned)t.dm * 16u, bar);
+                if (++xs == NS) xs = 0;
+            }
+        } else if (lane == 0) {
+            int es = 0;
+            for (int eb = 0; eb < a.nblocks; ++eb) {
+                observe(eb - NB);
+                const LinBlk t = blk[eb];
+                const unsigned vbytes = (unsigned)t.L * (unsigned)t.dm * 16u;
+                unsigned long long* bar = &efull[es];
+                mbar_arrive_expect_tx(bar, vbytes + (unsigned)(ML_FLAT * sizeof(LinEnt)));
+                tma_load_1d(flat + es * ML_FLAT, a.flat + (size_t)eb * ML_FLAT, (unsigned)(ML_FLAT * sizeof(LinEnt)), bar);
+                if (vbytes) tma_load_1d(ebuf + (size_t)es * a.ebuf_elems, a.val + t.val_off, vbytes, bar);
+                if (++es == NB) es = 0;
+            }
+        }
+        return;
+    }
+
+    // ================= compute warps =================
+    const int ls = lane >> 3, q = lane & 7;                 // state of the tile, row position inside the group
+    const int R = warp * 8 + q;
+    const long long sg = s_sb[ls];
+    const bool lv = sg >= 0 && R < dm_last;
+    const double sc = s_sc[ls];
+    const int nb = a.nblocks;
+    // x[bp][r_bp + d] from the ring (0 outside the block)
+    auto ring_x = [&](int bp, int slot, int d) -> double2 {
+        double2 v = make_double2(0.0, 0.0);
+        if (lv && bp < nb) {
+            const int dmp = blk[bp].dm;
+            const int r = R - ((dm_last - dmp) >> 1) + d;
+            if (r >= 0 && r < dmp) v = ring[(size_t)slot * slot_elems + (size_t)ls * a.dms + r];
+        }
+        return v;
+    };
+    double2 w[5][3];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) w[i][d] = make_double2(0.0, 0.0);
+    int waited = -1, ws = 0, wph = 0;
+    int bs = 0, es = 0, eph = 0;
+    double pre = 0.0, pim = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        // (the window reads block b+2 whatever the band width W <= 2 of the operator: the producer can always deliver it
+        //  without waiting for this block, NS >= W + 3)
+        const int newest = min(b + 2, nb - 1);
+        while (waited < newest) {
+            ++waited;
+            mbar_wait(&full[ws], (unsigned)wph);
+            if (++ws == NS) { ws = 0; wph ^= 1; }
+        }
+        mbar_wait(&efull[es], (unsigned)eph);
+        // ---- window: blocks b-2 .. b+2; block b+2 enters now (blocks 0 .. 2 at the first step)
+        if (b == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) w[2 + i][d] = ring_x(i, i % NS, d - 1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) w[i][d] = w[i + 1][d];
+            const int slot2 = (b + 2) % NS;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w[4][d] = ring_x(b + 2, slot2, d - 1);
+        }
+        const LinBlk bt = blk[b];
+        const int r = R - ((dm_last - bt.dm) >> 1);
+        const bool rowv = lv && r >= 0 && r < bt.dm;
+        const uint4 cm = *reinterpret_cast<const uint4*>(flat + es * ML_FLAT + (ML_FLAT - 1));
+        const unsigned cmw[4] = {cm.x, cm.y, cm.z, cm.w};
+        const double2* ev = ebuf + (size_t)es * a.ebuf_elems + (rowv ? r : 0);
+        double2 acc = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            double2 e[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int c = i * 3 + d;
+                const unsigned u = (cmw[c >> 2] >> (8 * (c & 3))) & 0xffu;   // warp-uniform
+                e[d] = make_double2(0.0, 0.0);
+                if (u != 0xffu && rowv) e[d] = ev[u * bt.dm];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double2 v = w[i][d];
+                if (d & 1) {
+                    acc2.x = fma(e[d].x, v.x, acc2.x);
+                    acc2.y = fma(e[d].x, v.y, acc2.y);
+                    acc2.x = fma(-e[d].y, v.y, acc2.x);
+                    acc2.y = fma(e[d].y, v.x, acc2.y);
+                } else {
+                    acc.x = fma(e[d].x, v.x, acc.x);
+                    acc.y = fma(e[d].x, v.y, acc.y);
+                    acc.x = fma(-e[d].y, v.y, acc.x);
+                    acc.y = fma(e[d].y, v.x, acc.y);
+                }
+            }
+        }
+        if (rowv) {
+            const double2 y = make_double2((acc.x + acc2.x) * sc, (acc.y + acc2.y) * sc);
+            if (Y != nullptr) Y[sg * ldy + bt.off + r] = y;
+            const double2 xb = w[2][1];
+            pre += y.x * xb.x + y.y * xb.y;
+            pim += y.x * xb.y - y.y * xb.x;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[bs]);                // this warp is finished with bra block b
+        if (++bs == NS) bs = 0;
+        if (++es == NB) { es = 0; eph ^= 1; }
+    }
+    if (pdot != nullptr && warp < ngroups) {
+        // the 8 row positions of a state are adjacent lanes: fixed-order reduction
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            pre += __shfl_xor_sync(0xffffffffu, pre, o);
+            pim += __shfl_xor_sync(0xffffffffu, pim, o);
+        }
+        if (q == 0 && sg >= 0) pdot[sg * npart + warp] = make_double2(pre, pim);
     }
 }
 
