@@ -815,7 +815,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                     // Both register-window kernels are opt-in (RMB_MW=1: k_matvec_mw, RMB_LINW=1: k_matvec_linw).  They are correct
                     // -- the whole GPU suite passes with either as the default -- but issue 3.4x the instructions of the ring
                     // kernel for the same work and are slower as they stand: 0.92 / 1.24-1.34 ms against 0.39 ms on the OCS
-                    // batch (profiles/r02_linw_notes.md)
+                    // batch (profiles/r02_lin_notes.md)
                     bool ok = W <= MW_DB;
                     std::vector<int> cshift(d->nblocks, 0);
                     for (int b = 0; b + 1 < d->nblocks; ++b) {
