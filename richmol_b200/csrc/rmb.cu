@@ -792,7 +792,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                     chunk0 += nch;
                     ubase = (ubase + nch * G) % ML_CWARPS;
                 }
-                op->lin_npart = chunk0;
+                op->lin_npart = ML_CWARPS / G;         // <w,v> partials per state: one per warp of the state's group
                 if ((rc = upload((LinBlk**)&op->d_lin_blk, lb.data(), lb.size()))) return rc;
                 RMB_CUDA(cudaMalloc(&op->d_lin_flat, (size_t)d->nblocks * ML_FLAT * sizeof(LinEnt)));
                 if ((rc = upload(&op->d_lin_val_off, val_off.data(), val_off.size()))) return rc;   // k_lin_entries

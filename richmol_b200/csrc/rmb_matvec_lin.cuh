@@ -18,7 +18,7 @@
 
 namespace rmb {
 
-constexpr int ML_CWARPS = 15;                        // compute warps
+constexpr int ML_CWARPS = 16;                        // compute warps (a power of two: chunk -> warp by masking)
 constexpr int ML_XPROD = 1;               // producer warps for the ket blocks (block j -> warp j % ML_XPROD)
 constexpr int ML_THREADS = (ML_CWARPS + ML_XPROD + 1) * 32;   // + producer warps (TMA bulk copies: ket blocks, entries)
 constexpr int ML_TS = 4;                             // states per thread for the 8-state tile (T / 2 in general)
@@ -282,41 +282,49 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
     }
 
     // ================= compute warps =================
-    int waited = -1;                                 // highest ket block whose arrival has been observed
+    // Warp w serves state group g = w % G for the whole kernel and, of every bra block, the 32-row chunks c with
+    // (chunk0 + c) % WPG == w / G.  <w,v> is accumulated per thread over all its units and reduced once per state at the end
+    // (one partial per state and warp of the group): the per-unit shuffle reductions were 20 % of the kernel's instructions.
+    constexpr int WPG = ML_CWARPS / G;               // warps per state group (a power of two)
+    static_assert(WPG * G == ML_CWARPS && (WPG & (WPG - 1)) == 0, "chunk -> warp mapping masks with WPG - 1");
+    const int g = warp % G, wi = warp / G;
+    const int tb = g * TS;
+    const char* ring_b = reinterpret_cast<const char*>(ring);
+    const unsigned st_bytes = (unsigned)a.dms * 16u;
+    const unsigned tb_bytes = (unsigned)tb * st_bytes;
+    double px[TS], py[TS];
+#pragma unroll
+    for (int t = 0; t < TS; ++t) px[t] = py[t] = 0.0;
     int ws = 0, wph = 0;                             // slot / phase of the next `full` barrier to observe
     int bs = 0;                                      // b % NS
     int es = 0, eph = 0;                             // b % NB and the phase of its `efull` barrier
-    const char* ring_b = reinterpret_cast<const char*>(ring);
-    const unsigned st_bytes = (unsigned)a.dms * 16u;
+    // Every warp observes every phase of every barrier in order, also for blocks in which it owns no unit: a parity wait is
+    // only defined for the current or the immediately preceding phase, and the waits are what keeps a warp without work from
+    // running ahead of the data.  Ket blocks 0 .. W-1 here, block b + W at the top of iteration b.
+    for (int j = 0; j < a.W && j < a.nblocks; ++j) {
+        mbar_wait(&full[ws], (unsigned)wph);
+        if (++ws == NS) { ws = 0; wph ^= 1; }
+    }
     for (int b = 0; b < a.nblocks; ++b) {
-        const LinBlk bt = blk[b];
-        const int dm1 = bt.dm;
-        const int nunits = ((dm1 + 31) >> 5) * G;
-        int u = warp - bt.ubase;                     // first unit of the block owned by this warp
-        if (u < 0) u += ML_CWARPS;
-        // Every warp observes every phase of every barrier in order, also for blocks in which it owns no unit:
-        // a parity wait is only defined for the current or the immediately preceding phase, and the waits are
-        // what keeps a warp without work from running ahead of the data (it would otherwise pass `done` for
-        // blocks the producer has not even requested and later mistake an old phase of a slot for the new one).
-        const int newest = min(b + a.W, a.nblocks - 1);
-        while (waited < newest) {
-            ++waited;
+        if (b + a.W < a.nblocks) {
             mbar_wait(&full[ws], (unsigned)wph);
             if (++ws == NS) { ws = 0; wph ^= 1; }
         }
         mbar_wait(&efull[es], (unsigned)eph);
-        if (u < nunits) {
+        const int4 bm = reinterpret_cast<const int4*>(blk + b)[1];          // dm, chunk0, -, L
+        const int dm1 = bm.x;
+        const int nch = (dm1 + 31) >> 5;
+        int c = (wi - bm.y) & (WPG - 1);             // first chunk of the block owned by this warp
+        if (c < nch) {
+            const long long boff = blk[b].off;
             const LinEnt* fl = flat + es * ML_FLAT;
             const double2* ev = ebuf + (size_t)es * a.ebuf_elems;
-            const int L = bt.L;
-            const double2* xbra = ring + (size_t)bs * slot_elems;
-            for (; u < nunits; u += ML_CWARPS) {
-                const int c = u / G, g = u - c * G;
+            const int L = bm.w;
+            const double2* xbra = ring + (size_t)bs * slot_elems + (size_t)tb * a.dms;
+            for (; c < nch; c += WPG) {
                 const int r = c * 32 + lane;
                 const bool rv = r < dm1;
                 const int rr = rv ? r : dm1 - 1;              // idle lanes repeat the last row (never stored)
-                const int tb = g * TS;
-                const unsigned tb_bytes = (unsigned)tb * st_bytes;
                 double2 acc[TS];
 #pragma unroll
                 for (int t = 0; t < TS; ++t) acc[t] = make_double2(0.0, 0.0);
@@ -337,26 +345,19 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
                         acc[t].y = fma(e.y, v[t].x, acc[t].y);
                     }
                 }
+                if (rv) {
 #pragma unroll
-                for (int t = 0; t < TS; ++t) {
-                    const long long sg = s_sb[tb + t];
-                    if (sg < 0) continue;                     // warp-uniform
-                    const double sc = s_sc[tb + t];
-                    const double2 y = make_double2(acc[t].x * sc, acc[t].y * sc);
-                    if (Y != nullptr && rv) Y[sg * ldy + bt.off + r] = y;    // lanes = consecutive rows
-                    if (pdot != nullptr) {
-                        double px = 0.0, py = 0.0;
-                        if (rv) {
-                            const double2 v = xbra[(size_t)(tb + t) * a.dms + r];
-                            px = y.x * v.x + y.y * v.y;
-                            py = y.x * v.y - y.y * v.x;
+                    for (int t = 0; t < TS; ++t) {
+                        const long long sg = s_sb[tb + t];
+                        if (sg < 0) continue;                     // warp-uniform
+                        const double sc = s_sc[tb + t];
+                        const double2 y = make_double2(acc[t].x * sc, acc[t].y * sc);
+                        if (Y != nullptr) Y[sg * ldy + boff + r] = y;       // lanes = consecutive rows
+                        if (pdot != nullptr) {
+                            const double2 v = xbra[(size_t)t * a.dms + r];
+                            px[t] = fma(y.x, v.x, fma(y.y, v.y, px[t]));
+                            py[t] = fma(y.x, v.y, fma(-y.y, v.x, py[t]));
                         }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            px += __shfl_down_sync(0xffffffffu, px, o);
-                            py += __shfl_down_sync(0xffffffffu, py, o);
-                        }
-                        if (lane == 0) pdot[sg * npart + bt.chunk0 + c] = make_double2(px, py);
                     }
                 }
             }
@@ -366,9 +367,22 @@ k_matvec_lin(const LinArgs a, const double2* __restrict__ X, double2* __restrict
         if (++bs == NS) bs = 0;
         if (++es == NB) { es = 0; eph ^= 1; }
     }
+    if (pdot != nullptr) {
+        // fixed-order reduction: the lanes of the warp; the host sums the WPG partials of a state in index order
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            double a0 = px[t], a1 = py[t];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            }
+            const long long sg = s_sb[tb + t];
+            if (lane == 0 && sg >= 0) pdot[sg * npart + wi] = make_double2(a0, a1);
+        }
+    }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
 // k_matvec_linw: the same ring / producer protocol as k_matvec_lin for a tile of 4 states, but the compute warps keep
 // the ket elements in a REGISTER WINDOW.  Warp g owns the 8 row positions R = 8g .. 8g+7 (counted in the last, largest
 // block: blocks are ordered by J with symmetric m ranges, so the row of the same m in block b is
