@@ -452,7 +452,6 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         it.nst = best_nst;
                         it.mt = best_mt;
                         it.desc_off = (int)gdesc.size();
-                        it.pad = 0;
                         int xbe = 16, ktd = 2;
                         for (int p = it.p_begin; p < it.p_end; ++p) {
                             const ProdD& q = op->h_prods[p];
@@ -499,8 +498,15 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                         } else {
                             it.kt_off = found->second;
                         }
-                        op->matvecG_smem = std::max(op->matvecG_smem,
-                                                    md_smem_bytes(it.x_elems, it.mt, it.kt_doubles, it.p_end - it.p_begin));
+                        // the CTA owns the SM anyway (416 threads x 128 registers): small items use the shared memory the large
+                        // ones need for a deeper pipeline (their products compute faster than a bulk copy takes to land)
+                        it.nstages = MD_STAGES;
+                        while (it.nstages < MD_STAGES_MAX && it.nstages < it.p_end - it.p_begin &&
+                               md_smem_bytes(it.x_elems, it.mt, it.kt_doubles, it.p_end - it.p_begin, it.nstages + 1) <= MD_SMEM_DEEP)
+                            ++it.nstages;
+                        if (const char* e = getenv("RMB_DMMA_STAGES")) it.nstages = std::min(it.nstages, std::max(MD_STAGES, atoi(e)));
+                        op->matvecG_smem = std::max(op->matvecG_smem, md_smem_bytes(it.x_elems, it.mt, it.kt_doubles,
+                                                                                    it.p_end - it.p_begin, it.nstages));
                         itemsG.push_back(it);
                     }
                 continue;

@@ -24,9 +24,11 @@ namespace rmb {
 
 constexpr int MD_MMA_WARPS = 12;
 constexpr int MD_THREADS = (MD_MMA_WARPS + 1) * 32;   // + one producer warp
-constexpr int MD_STAGES = 2;
+constexpr int MD_STAGES = 2;                          // products in flight: minimum ...
+constexpr int MD_STAGES_MAX = 4;                      // ... and maximum per item (ItemD2::nstages: as many as fit the shared memory)
 constexpr int MD_NTMAX = 8;                           // n-tiles of 8 columns -> <= 64 columns per item
 constexpr size_t MD_SMEM_MAX = 226 * 1024;
+constexpr size_t MD_SMEM_DEEP = 222 * 1024;           // budget for stages beyond MD_STAGES (227 KB per CTA minus the static arrays)
 
 struct ItemD2 {
     long long bra_off;
@@ -42,16 +44,16 @@ struct ItemD2 {
     int desc_off;            // first ProdS descriptor
     int x_elems;             // double2 elements of the ket-row area of one stage
     int kt_doubles;          // doubles of the K^T area of one stage
-    int pad;
+    int nstages;             // pipeline stages of this item (MD_STAGES .. MD_STAGES_MAX)
 };
 
 // stage layout: [X: x_elems double2][MF: MV2_NDMAX * 8*mt MfEntry][K^T: kt_doubles double]
 __host__ __device__ inline size_t md_stage_bytes(int x_elems, int mt, int kt_doubles) {
     return (size_t)x_elems * 16 + (size_t)MV2_NDMAX * 8 * mt * sizeof(MfEntry) + (size_t)kt_doubles * 8;
 }
-__host__ __device__ inline size_t md_smem_bytes(int x_elems, int mt, int kt_doubles, int nprod) {
-    return MD_STAGES * md_stage_bytes(x_elems, mt, kt_doubles) + (size_t)nprod * sizeof(ProdS) +
-           (size_t)4 * MD_MMA_WARPS * 8 + 2 * MD_STAGES * 8 + 128;
+__host__ __device__ inline size_t md_smem_bytes(int x_elems, int mt, int kt_doubles, int nprod, int nstages = MD_STAGES) {
+    return nstages * md_stage_bytes(x_elems, mt, kt_doubles) + (size_t)nprod * sizeof(ProdS) +
+           (size_t)4 * MD_MMA_WARPS * 8 + 2 * MD_STAGES_MAX * 8 + 128;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -124,10 +126,11 @@ __device__ __forceinline__ void md_body(const ItemD2& it, const ProdS* __restric
     const int np = it.p_end - it.p_begin;
     const size_t stage_bytes = md_stage_bytes(it.x_elems, it.mt, it.kt_doubles);
     unsigned char* stage0 = rmb_dsmem;
-    ProdS* sp = reinterpret_cast<ProdS*>(rmb_dsmem + MD_STAGES * stage_bytes);
+    const int NSTG = it.nstages;
+    ProdS* sp = reinterpret_cast<ProdS*>(rmb_dsmem + NSTG * stage_bytes);
     double* red = reinterpret_cast<double*>(sp + np);                                 // [2 (tile parity)][2][MD_MMA_WARPS]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(red + 4 * MD_MMA_WARPS);
-    unsigned long long* empty = full + MD_STAGES;
+    unsigned long long* empty = full + MD_STAGES_MAX;
     __shared__ int s_valid[MV2_TILES_MAX][MD_MMA_WARPS];      // state s of tile t is present and active
     __shared__ int s_nact[MV2_TILES_MAX];
 
@@ -139,7 +142,7 @@ __device__ __forceinline__ void md_body(const ItemD2& it, const ProdS* __restric
         s_valid[t][s] = (s < it.nst && sg < nstates && (active == nullptr || active[sg])) ? 1 : 0;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < MD_STAGES; ++i) {
+        for (int i = 0; i < NSTG; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], MD_MMA_WARPS);
         }
@@ -168,7 +171,7 @@ __device__ __forceinline__ void md_body(const ItemD2& it, const ProdS* __restric
                 const int k2p = (d.dk2 + 3) & ~3;
                 const unsigned ktbytes = (unsigned)(k2p * it.ldk) * 8u;
                 if (d.nnz > 0 && d.nr > 0) {
-                    if (fill >= MD_STAGES) mbar_wait(&empty[stage], (unsigned)(ph ^ 1));   // consumers released the stage
+                    if (fill >= NSTG) mbar_wait(&empty[stage], (unsigned)(ph ^ 1));   // consumers released the stage
                     unsigned char* st = stage0 + (size_t)stage * stage_bytes;
                     double2* xst = reinterpret_cast<double2*>(st);
                     MfEntry* mfe = reinterpret_cast<MfEntry*>(st + (size_t)it.x_elems * 16);
@@ -191,7 +194,7 @@ __device__ __forceinline__ void md_body(const ItemD2& it, const ProdS* __restric
                         tma_load_1d(kst, ktpool + ktoff, ktbytes, &full[stage]);
                     }
                     ++fill;
-                    if (++stage == MD_STAGES) { stage = 0; ph ^= 1; }
+                    if (++stage == NSTG) { stage = 0; ph ^= 1; }
                 }
                 ktoff += (long long)k2p * it.ldk;
             }
@@ -251,7 +254,7 @@ __device__ __forceinline__ void md_body(const ItemD2& it, const ProdS* __restric
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == MD_STAGES) { stage = 0; ph ^= 1; }
+            if (++stage == NSTG) { stage = 0; ph ^= 1; }
         }
 
         // ---- epilogue: lane holds C[tile row arow][cols 2*kq, 2*kq+1] of every n-tile
