@@ -37,3 +37,5 @@ for r in d["workloads"]:
 print(d.get("cpu_baseline"))
 PY
 ls -la $out | grep ${tag}_
+# device timelines of the bench step (CUPTI; shares and gaps only)
+for wl in h2s h2o ocs_batch; do timeout 400 python tools/gpu_timeline.py $wl 4 2>&1 | grep -v "Warn\|_warn_once"; done > $out/${tag}_step_timeline.txt
