@@ -27,6 +27,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     return RMB_ERR_CUDA;
 }
 
+// dynamic shared memory k_lanczos_fused has been allowed so far (13 KB of static shared memory come on top)
+static size_t g_fused_smem = 16 * 1024;
+
 template <typename T>
 static int upload(T** dptr, const T* src, size_t count) {
     *dptr = nullptr;
@@ -720,7 +723,6 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
             if ((rc = upload(&op->d_blk_begin, bra_begin.data(), bra_begin.size()))) return rc;
             if ((rc = upload(&op->d_blk_off, boff.data(), boff.size()))) return rc;
             if ((rc = upload(&op->d_blk_dm, d->blk_dm, (size_t)d->nblocks))) return rc;
-            static size_t g_fused_smem = 16 * 1024;   // 13 KB of static shared memory come on top
             if (fused_smem > g_fused_smem) {
                 RMB_CUDA(cudaFuncSetAttribute(k_lanczos_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
                 g_fused_smem = fused_smem;
@@ -774,6 +776,7 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
                 }
             }
             if (op->lin_ok && op->nent >= (1ll << 31)) op->lin_ok = false;
+            op->fused_lcap = op->lin_ok ? maxL : 0;
             if (op->lin_ok) {
                 if (!op->d_blk_begin) {
                     std::vector<long long> boff(d->nblocks);
@@ -1621,9 +1624,23 @@ static int propagate_device(rmb_operator* op, cplx* psi, long long nstates, long
             fa.lin_flat = (const LinEnt*)op->d_lin_flat;
             fa.lin_val = op->d_lin_val;
         }
+        // entry lists in shared memory behind the vectors when they fit (they share the room of the product descriptors)
+        size_t fused_dyn = (size_t)3 * n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd);
+        fa.nblocks = op->nblocks;
+        fa.lin_lcap = 0;
+        if (fa.lin_blk && op->fused_lcap > 0) {
+            const size_t with_tab = (size_t)3 * n * sizeof(cplx) + fused_lin_table_bytes(op->nblocks, op->fused_lcap);
+            if (with_tab <= 210 * 1024) {
+                fa.lin_lcap = op->fused_lcap;
+                fused_dyn = std::max(fused_dyn, with_tab);
+                if (fused_dyn > g_fused_smem) {
+                    RMB_CUDA(cudaFuncSetAttribute(k_lanczos_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn));
+                    g_fused_smem = fused_dyn;
+                }
+            }
+        }
         // the history slabs are indexed [slab][state * n + i] with the leading dimension of this batch
-        k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS,
-                          (size_t)3 * n * sizeof(cplx) + (size_t)op->nprod * sizeof(FusedProd), st>>>(fa, nstates);
+        k_lanczos_fused<<<(unsigned)nstates, FUSED_THREADS, fused_dyn, st>>>(fa, nstates);
         RMB_CUDA(cudaGetLastError());
         op->n_launches++;
         op->n_iterations++;

@@ -46,7 +46,16 @@ struct FusedArgs {
     const LinEnt* lin_flat;      // [nblocks][ML_FLAT]; record 0 = header (count), LinEnt::pad = ket block
     const cplx* lin_val;
     int gram_kmax;               // iterations whose convergence metric uses the Gram diagonal (0: always explicit)
+    int nblocks;
+    int lin_lcap;                // > 0: the entry lists (<= lin_lcap entries per block) and the per-block table are staged in
+                                 // shared memory behind the three vectors (fused_lin_table_bytes)
 };
+
+// entry of a staged list: offset of the ket block in the state vector, diagonal offset (col - row), rows of the ket block
+struct __align__(16) FusedEnt { int koff, doff, dm2, pad; };
+__host__ __device__ inline size_t fused_lin_table_bytes(int nblocks, int lcap) {
+    return (size_t)nblocks * ((size_t)lcap * sizeof(FusedEnt) + 16);
+}
 
 template <int NT>
 __device__ __forceinline__ double block_sum_all(double v, double* sm) {
@@ -150,6 +159,13 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
     cplx* psi = a.psi + s * a.ld;
     const long long n = a.n;
     const bool lin = a.lin_blk != nullptr;
+    // -DRMB_FUSED_TRACE: thread 0 of CTA 0 prints the cycles of every phase of the step (tools/ab_build.sh, RMB_LIB)
+#ifdef RMB_FUSED_TRACE
+    long long tr_t0 = clock64(), tr_mv = 0, tr_up = 0, tr_ex = 0, tr_hist = 0, tr_rot = 0, tr_last;
+#define TR(acc) { const long long tr_now = clock64(); acc += tr_now - tr_last; tr_last = tr_now; }
+#else
+#define TR(acc)
+#endif
 
     // rows of this thread: block and position inside it (fixed for the whole step)
     int rb[FUSED_ROWS], rm[FUSED_ROWS];
@@ -171,6 +187,31 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         vk[i] = v;
         a.slabs[0][s * n + i] = v;
         g0 += cabs2(v);
+    }
+    const bool staged = lin && a.lin_lcap > 0;
+    FusedEnt* s_ent = reinterpret_cast<FusedEnt*>(w + a.n);                          // [nblocks][lin_lcap]
+    long long* s_voff = reinterpret_cast<long long*>(s_ent + (size_t)a.nblocks * a.lin_lcap);   // [nblocks]
+    int* s_bdm = reinterpret_cast<int*>(s_voff + a.nblocks);                         // [nblocks]
+    int* s_bL = s_bdm + a.nblocks;                                                   // [nblocks]
+    if (staged) {
+        for (int idx = threadIdx.x; idx < a.nblocks * a.lin_lcap; idx += FUSED_THREADS) {
+            const int b = idx / a.lin_lcap, j = idx - b * a.lin_lcap;
+            const LinEnt* fl = a.lin_flat + (size_t)b * ML_FLAT;
+            FusedEnt f = {0, 0, 1, 0};
+            if (j < (int)fl[0].xbyte) {
+                const LinEnt g = fl[1 + j];
+                f.koff = (int)a.blk_off[g.pad];
+                f.doff = g.doff;
+                f.dm2 = g.dm2;
+            }
+            s_ent[idx] = f;
+        }
+        for (int b = threadIdx.x; b < a.nblocks; b += FUSED_THREADS) {
+            const LinBlk bt = a.lin_blk[b];
+            s_voff[b] = bt.val_off;
+            s_bdm[b] = bt.dm;
+            s_bL[b] = min((int)a.lin_flat[(size_t)b * ML_FLAT].xbyte, a.lin_lcap);
+        }
     }
     if (!lin)
         for (int p = threadIdx.x; p < a.nprod; p += FUSED_THREADS) {
@@ -196,10 +237,53 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
 
     int k = 0, last = 0;
     bool hit_max = (a.maxorder <= 1);
+#ifdef RMB_FUSED_TRACE
+    const long long tr_init = clock64() - tr_t0;
+    tr_last = clock64();
+#endif
     for (;; ++k) {
         // ---- w = H V_k and alpha_k = vdot(w, V_k) in one pass
         double re = 0, im = 0;
-        if (lin) {
+        if (lin && staged) {
+            // entry lists and block table in shared memory: the only global loads of a row are its entry values, eight
+            // independent ones per trip (before: block record -> list header -> entry -> ket offset, four dependent L2 round
+            // trips per trip of four entries, ~5.6 k cycles per row)
+#pragma unroll
+            for (int r = 0; r < FUSED_ROWS; ++r) {
+                const long long i = threadIdx.x + (long long)r * FUSED_THREADS;
+                if (i < n) {
+                    const int b = rb[r], m = rm[r];
+                    const int L = s_bL[b], dm = s_bdm[b];
+                    const FusedEnt* ent = s_ent + b * a.lin_lcap;
+                    const cplx* ev = a.lin_val + s_voff[b] + m;
+                    cplx acc = make_double2(0.0, 0.0);
+                    for (int j0 = 0; j0 < L; j0 += 8) {
+                        cplx e[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            e[u] = make_double2(0.0, 0.0);
+                            if (j0 + u < L) e[u] = ev[(long long)(j0 + u) * dm];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (j0 + u < L) {
+                                const FusedEnt f = ent[j0 + u];
+                                const int col = min(max(m + f.doff, 0), f.dm2 - 1);   // outside the ket block e is zero
+                                const cplx v = vk[f.koff + col];
+                                acc.x = fma(e[u].x, v.x, acc.x);
+                                acc.y = fma(e[u].x, v.y, acc.y);
+                                acc.x = fma(-e[u].y, v.y, acc.x);
+                                acc.y = fma(e[u].y, v.x, acc.y);
+                            }
+                        }
+                    }
+                    w[i] = acc;
+                    const cplx y = vk[i];
+                    re += acc.x * y.x + acc.y * y.y;
+                    im += acc.x * y.y - acc.y * y.x;
+                }
+            }
+        } else if (lin) {
 #pragma unroll
             for (int r = 0; r < FUSED_ROWS; ++r) {
                 const long long i = threadIdx.x + (long long)r * FUSED_THREADS;
@@ -246,6 +330,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
             }
         }
         const double2 al = block_sum2_all(re, im, red2);
+        TR(tr_mv)
         const cplx alpha = make_double2(al.x, al.y);
         const double beta = s_beta[k];
         if (threadIdx.x == 0) s_alpha[k] = alpha;
@@ -264,6 +349,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
             s_g[k + 1] = (beta_next != 0.0) ? nr / (beta_next * beta_next) : 1.0;      // <V_{k+1}, V_{k+1}>
         }
         __syncthreads();
+        TR(tr_up)
         const bool use_gram = k < a.gram_kmax;
         bool done = false;
         if (k > 0) {
@@ -280,6 +366,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
                 }
                 cv = warp_sum(cv);
                 if (threadIdx.x == 0) s_conv = cv;                  // Gram-diagonal form of the metric
+                TR(tr_ex)
             }
             if (!use_gram) {
                 // explicit evaluation over the Krylov history (many vectors: orthogonality is no longer a given)
@@ -306,6 +393,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
                 a.slabs[k + 1][s * n + i] = make_double2(r.x / beta_next, r.y / beta_next);
             }
         __syncthreads();
+        TR(tr_hist)
         if (k > 0) {
             last = k;
             if (k == a.maxorder - 1) { hit_max = true; done = true; }
@@ -354,6 +442,7 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
             }
         }
         __syncthreads();
+        TR(tr_rot)
     }
     // psi = ph * u_k,  u_k = sum_i c_i V_i  (u_0 = V_0 when the loop never ran)
     __syncthreads();
@@ -372,6 +461,14 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         a.order[s] = last;
         if (hit_max) atomicExch(a.ctrl, 1);
     }
+#ifdef RMB_FUSED_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long tr_end = clock64();
+        printf("[fused] n %lld order %d cycles: total %lld init %lld matvec+alpha %lld update+norm %lld expm(warp0) %lld hist+wait %lld "
+               "rotate %lld final %lld\n", n, last, tr_end - tr_t0, tr_init, tr_mv, tr_up, tr_ex, tr_hist, tr_rot, tr_end - tr_last);
+    }
+#endif
 }
 
 }  // namespace rmb

@@ -315,19 +315,80 @@ k_dot(const cplx* __restrict__ w, const cplx* __restrict__ Vk, long long ldv, lo
 // First column of exp(fac * T), T symmetric tridiagonal (k+1 x k+1) with diagonal alpha[0..k] and
 // off-diagonal beta[1..k]; scaled Taylor series applied to e_0 (replaces scipy.sparse.linalg.expm,
 // tdse.py:474).  One warp; y/term/tmp are shared-memory arrays of >= n entries.
+// Register path of warp_expm_col0 for n <= 32: lane i owns row i of the tridiagonal T (alpha_i and its two couplings) and
+// element i of the running term / sum; the neighbours' term elements come by shuffle, the scale factors 1 / (j nsub) are
+// computed once per call (lane L: j = L + 1 and L + 33) and broadcast, and the stop test runs every fourth term -- the same
+// series, sub-stepping and stop criterion as the shared-memory path below, which needed ~600 cycles per term (two
+// __syncwarp, two warp_max, a division, six shared-memory round trips) and made the small exponential 85 % of a fused
+// single-state step at high Lanczos order (one warp works, fifteen wait).
+__device__ __forceinline__ void warp_expm_col0_reg(int n, const cplx* __restrict__ alpha, const double* __restrict__ beta,
+                                                   cplx fac, int nsub, double mu, cplx phase, cplx* y_out) {
+    const int lane = threadIdx.x & 31;
+    const bool in = lane < n;
+    const cplx a = in ? make_double2(alpha[lane].x - mu, alpha[lane].y) : make_double2(0.0, 0.0);
+    const double bl = (in && lane > 0) ? beta[lane] : 0.0;
+    const double bu = (in && lane + 1 < n) ? beta[lane + 1] : 0.0;
+    const double sc_lo = 1.0 / ((double)(lane + 1) * (double)nsub);
+    const double sc_hi = 1.0 / ((double)(lane + 33) * (double)nsub);
+    cplx y = make_double2(lane == 0 ? 1.0 : 0.0, 0.0);
+    for (int sub = 0; sub < nsub; ++sub) {
+        cplx term = y;
+        for (int j = 1; j <= 60; ++j) {
+            const double sc = __shfl_sync(0xffffffffu, j <= 32 ? sc_lo : sc_hi, (j - 1) & 31);
+            const cplx f = make_double2(fac.x * sc, fac.y * sc);
+            const double tmx = __shfl_up_sync(0xffffffffu, term.x, 1), tmy = __shfl_up_sync(0xffffffffu, term.y, 1);
+            const double tpx = __shfl_down_sync(0xffffffffu, term.x, 1), tpy = __shfl_down_sync(0xffffffffu, term.y, 1);
+            cplx t = cmul(a, term);
+            if (lane > 0) { t.x += bl * tmx; t.y += bl * tmy; }
+            if (lane + 1 < n) { t.x += bu * tpx; t.y += bu * tpy; }
+            t = cmul(f, t);
+            y = cadd(y, t);
+            term = t;
+            if ((j & 3) == 0 || j == 60) {
+                const double tmax = warp_max(fmax(fabs(t.x), fabs(t.y)));
+                const double ymax = warp_max(fmax(fabs(y.x), fabs(y.y)));
+                if (!(tmax > 1e-19 * ymax)) break;
+            }
+        }
+    }
+    if (in) y_out[lane] = cmul(phase, y);
+    __syncwarp();
+}
+
+// c = expm(fac T)[:, 0] for the Hermitian tridiagonal T (diagonal alpha, off-diagonal beta) by one warp: Taylor series of
+// nsub sub-steps.  The common part mu of the diagonal (the centre of T's Gershgorin interval: the isotropic shift of the
+// interaction, which dominates ||T|| for polarisability Hamiltonians) is split off as the scalar exp(fac mu), so that the
+// series runs on T - mu with a spectral bound of half the interval: fewer sub-steps AND less cancellation; sub-steps of norm
+// <= EXPM_THETA.
+constexpr double EXPM_THETA = 2.0;
 __device__ void warp_expm_col0(int n, const cplx* __restrict__ alpha, const double* __restrict__ beta,
                                cplx fac, cplx* y, cplx* term, cplx* tmp) {
     const int lane = threadIdx.x & 31;
-    double loc = 0;
+    double lo = 1e300, hi = -1e300, im = 0.0;
     for (int i = lane; i < n; i += 32) {
-        double cs = hypot(alpha[i].x, alpha[i].y);
-        if (i > 0) cs += fabs(beta[i]);
-        if (i + 1 < n) cs += fabs(beta[i + 1]);
-        loc = fmax(loc, cs);
+        double r = 0.0;
+        if (i > 0) r += fabs(beta[i]);
+        if (i + 1 < n) r += fabs(beta[i + 1]);
+        lo = fmin(lo, alpha[i].x - r);
+        hi = fmax(hi, alpha[i].x + r);
+        im = fmax(im, fabs(alpha[i].y));
     }
-    const double nrm = warp_max(loc) * hypot(fac.x, fac.y);
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    im = warp_max(im);
+    const double mu = 0.5 * (lo + hi);
+    const double nrm = (0.5 * (hi - lo) + im) * hypot(fac.x, fac.y);
     int nsub = 1;
-    if (nrm > 1.0 && nrm < 1e7) nsub = (int)ceil(nrm);
+    if (nrm > EXPM_THETA && nrm < 1e7) nsub = (int)ceil(nrm / EXPM_THETA);
+    // exp(fac mu)
+    const double pm = exp(fac.x * mu);
+    double ps, pc;
+    sincos(fac.y * mu, &ps, &pc);
+    const cplx phase = make_double2(pm * pc, pm * ps);
+    if (n <= 32) {
+        warp_expm_col0_reg(n, alpha, beta, fac, nsub, mu, phase, y);
+        return;
+    }
     for (int i = lane; i < n; i += 32) y[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
     __syncwarp();
     for (int sub = 0; sub < nsub; ++sub) {
@@ -338,7 +399,7 @@ __device__ void warp_expm_col0(int n, const cplx* __restrict__ alpha, const doub
             const cplx f = make_double2(fac.x * sc, fac.y * sc);
             double tmax = 0, ymax = 0;
             for (int i = lane; i < n; i += 32) {
-                cplx t = cmul(alpha[i], term[i]);
+                cplx t = cmul(make_double2(alpha[i].x - mu, alpha[i].y), term[i]);
                 if (i > 0) { t.x += beta[i] * term[i - 1].x; t.y += beta[i] * term[i - 1].y; }
                 if (i + 1 < n) { t.x += beta[i + 1] * term[i + 1].x; t.y += beta[i + 1] * term[i + 1].y; }
                 t = cmul(f, t);
@@ -356,6 +417,8 @@ __device__ void warp_expm_col0(int n, const cplx* __restrict__ alpha, const doub
             if (!(tmax > 1e-19 * ymax)) break;
         }
     }
+    for (int i = lane; i < n; i += 32) y[i] = cmul(phase, y[i]);
+    __syncwarp();
 }
 
 // per state (one warp), after the matvec of iteration k:
