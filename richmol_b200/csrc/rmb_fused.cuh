@@ -390,7 +390,9 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         if (!fallback)
             for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
                 const cplx r = w[i];
-                a.slabs[k + 1][s * n + i] = make_double2(r.x / beta_next, r.y / beta_next);
+                const cplx q = make_double2(r.x / beta_next, r.y / beta_next);
+                a.slabs[k + 1][s * n + i] = q;
+                w[i] = q;                                  // becomes V_{k+1} by the pointer rotation below
             }
         __syncthreads();
         TR(tr_hist)
@@ -404,11 +406,10 @@ k_lanczos_fused(const FusedArgs a, long long nstates) {
         if (done) break;
         // rotate: V_{k-1} <- V_k, V_k <- V_{k+1}
         if (!fallback) {
-            for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
-                const cplx r = w[i];
-                vkm1[i] = vk[i];
-                vk[i] = make_double2(r.x / beta_next, r.y / beta_next);
-            }
+            cplx* const t = vkm1;                          // no copies: the buffer of V_{k-1} takes the next H V
+            vkm1 = vk;
+            vk = w;
+            w = t;
         } else {
             // zero-beta fallback (tdse.py:459-465): Gram-Schmidt of the all-ones vector against V_0..V_k
             for (long long i = threadIdx.x; i < n; i += FUSED_THREADS) {
