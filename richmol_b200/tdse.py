@@ -221,6 +221,9 @@ class TDSE():
         o = getattr(self, "_orders", None)
         if isinstance(o, tuple):
             pin, nst, stream = o
+            if isinstance(stream, int):                   # raw cudaStream_t of the step (no Stream object per step)
+                import torch
+                stream = torch.cuda.ExternalStream(stream) if stream else torch.cuda.default_stream()
             stream.synchronize()
             o = pin[:nst].numpy().copy()
             self._orders = o
@@ -321,7 +324,7 @@ class TDSE():
             status = lib.rmb_propagate_step(
                 op.handle, out.data_ptr(), nst, N, exp_fac.real, exp_fac.imag, float(tol), 100,
                 ph_ptr, int(skip), pin.data_ptr(), stream)
-            self._orders = (pin, nst, torch.cuda.current_stream(out.device))
+            self._orders = (pin, nst, int(stream))
             _lib.check(status)
             return out
 
