@@ -610,7 +610,11 @@ def gpu_workload(w, args, headline, ctx):
         return tdse
 
     tdse = new_tdse()
-    obs = torch.zeros(1, dtype=torch.complex128, device=dev)
+    # ensemble <cos^2 theta>: per-step shard sums collected in a small device ring, all-reduced every OBS_EVERY steps (double
+    # buffered, asynchronous): the path's only collective, off the critical path of the latency-bound workloads
+    OBS_EVERY = 16
+    obs_ring = [torch.zeros(OBS_EVERY, dtype=torch.complex128, device=dev) for _ in range(2)]
+    obs_slot = [0, 0]                                              # ring in use, next slot
     pending = [None]
 
     def apply_fields(i):
@@ -625,14 +629,24 @@ def gpu_workload(w, args, headline, ctx):
         v, _ = tdse.update(hamiltonian(tensors), v, H0=h0, inplace=True)
         if cos2 is not None:
             ev = expectation(cos2, v)
-            if pending[0] is not None:
-                pending[0].wait()                                  # last step's all-reduce, overlapped with this step
-            torch.sum(ev, dim=0, keepdim=True, out=obs)            # <cos^2 theta> - 1/3 of this shard
-            if world > 1 and w.scaling != "replicas":
-                pending[0] = dist.all_reduce(torch.view_as_real(obs), async_op=True)   # the path's only collective
+            ring, slot = obs_ring[obs_slot[0]], obs_slot[1]
+            torch.sum(ev, dim=0, keepdim=True, out=ring[slot:slot + 1])     # <cos^2 theta> - 1/3 of this shard
+            obs_slot[1] = slot + 1
+            if obs_slot[1] == OBS_EVERY:
+                flush_obs()
         return v
 
+    def flush_obs():
+        if pending[0] is not None:
+            pending[0].wait()                                      # the previous block's all-reduce, overlapped with 16 steps
+            pending[0] = None
+        if obs_slot[1] > 0 and world > 1 and w.scaling != "replicas":
+            pending[0] = dist.all_reduce(torch.view_as_real(obs_ring[obs_slot[0]]), async_op=True)
+        obs_slot[0] ^= 1
+        obs_slot[1] = 0
+
     def barrier():
+        flush_obs()
         if pending[0] is not None:
             pending[0].wait()
             pending[0] = None
@@ -672,6 +686,7 @@ def gpu_workload(w, args, headline, ctx):
     e0.record()
     for i in range(warmup, warmup + steps):
         vecs = step(i, vecs)
+    flush_obs()                                                    # the last (partial) block of observables is reduced inside the timed region
     if pending[0] is not None:
         pending[0].wait()
         pending[0] = None
