@@ -183,6 +183,12 @@ int32_t rmb_operator_info(const rmb_operator* op, int64_t* out8);
  * pref = 1 the primitive K tensor over |J,k>.                                                               */
 int32_t rmb_threej_band(int32_t j1, int32_t j2, int32_t omega, int32_t ncoef, const double* coef_host, double pref,
                         double* out_host, void* stream);
+/* The small exponential of the Lanczos loop on its own (richmol/tdse.py:474, `expm(fac * T_k)[:, 0]` via scipy there): nmat
+ * Hermitian tridiagonal matrices of order n (n <= 128), diagonal alpha[mat][n] (complex), off-diagonal beta[mat][n] (real,
+ * beta[mat][i] couples i-1 and i, beta[mat][0] unused), out[mat][n] complex; host buffers, one warp per matrix -- the same
+ * device function the propagation kernels call (registers for n <= 32, shared memory above).  For tests.        */
+int32_t rmb_small_expm(int32_t nmat, int32_t n, const double* alpha_host, const double* beta_host, double fac_re,
+                       double fac_im, double* out_host, void* stream);
 /* FP64 roofline denominators measured on the current device (MEASURED_PEAKS.json has no FP64 entry):
  * register-resident DFMA and DMMA (mma.sync.m8n8k4.f64) loops over all SMs, best of 3, TFLOP/s.    */
 int32_t rmb_fp64_peak(double* dfma_tflops, double* dmma_tflops, void* stream);

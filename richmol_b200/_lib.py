@@ -69,6 +69,8 @@ SYMBOLS = {
     "rmb_matvec_timing": (C.c_int32, [C.c_void_p, C.c_int32, c_f64p, c_i64p]),
     "rmb_operator_info": (C.c_int32, [C.c_void_p, c_i64p]),
     "rmb_fp64_peak": (C.c_int32, [c_f64p, c_f64p, C.c_void_p]),
+    "rmb_small_expm": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                   C.c_void_p]),
     "rmb_threej_band": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p,
                                     C.c_void_p]),
 }

@@ -2162,6 +2162,34 @@ int32_t rmb_threej_band(int32_t j1, int32_t j2, int32_t omega, int32_t ncoef, co
     return RMB_OK;
 }
 
+int32_t rmb_small_expm(int32_t nmat, int32_t n, const double* alpha_host, const double* beta_host, double fac_re,
+                       double fac_im, double* out_host, void* stream) {
+    if (nmat <= 0 || n < 1 || n > MAX_ORDER_SMEM || !alpha_host || !beta_host || !out_host) {
+        set_error("small_expm: bad arguments (1 <= n <= 128)");
+        return RMB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cnt = (size_t)nmat * n;
+    cplx *d_a = nullptr, *d_o = nullptr;
+    double* d_b = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_a, cnt * sizeof(cplx));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, cnt * sizeof(cplx));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_b, cnt * sizeof(double));
+    if (e == cudaSuccess) {
+        cudaMemcpyAsync(d_a, alpha_host, cnt * sizeof(cplx), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_b, beta_host, cnt * sizeof(double), cudaMemcpyHostToDevice, st);
+        k_small_expm<<<(unsigned)nmat, 32, 0, st>>>(n, d_a, d_b, make_double2(fac_re, fac_im), d_o);
+        cudaMemcpyAsync(out_host, d_o, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_a);
+    cudaFree(d_o);
+    cudaFree(d_b);
+    if (e != cudaSuccess) return cuda_fail(e, "small_expm");
+    RMB_CUDA(cudaGetLastError());
+    return RMB_OK;
+}
+
 int32_t rmb_operator_info(const rmb_operator* op, int64_t* out8) {
     if (!op || !out8) return RMB_ERR_INVALID;
     out8[0] = op->nitems2;

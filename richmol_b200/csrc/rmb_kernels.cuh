@@ -421,6 +421,23 @@ __device__ void warp_expm_col0(int n, const cplx* __restrict__ alpha, const doub
     __syncwarp();
 }
 
+// rmb_small_expm: one warp per matrix
+__global__ void __launch_bounds__(32)
+k_small_expm(int n, const cplx* __restrict__ alpha, const double* __restrict__ beta, cplx fac, cplx* __restrict__ out) {
+    __shared__ double2 y[MAX_ORDER_SMEM], term[MAX_ORDER_SMEM], tmp[MAX_ORDER_SMEM];
+    __shared__ double2 sa[MAX_ORDER_SMEM];
+    __shared__ double sb[MAX_ORDER_SMEM];
+    const long long mat = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += 32) {
+        sa[i] = alpha[mat * n + i];
+        sb[i] = beta[mat * n + i];
+    }
+    __syncwarp();
+    warp_expm_col0(n, sa, sb, fac, y, term, tmp);
+    __syncwarp();
+    for (int i = threadIdx.x; i < n; i += 32) out[mat * n + i] = y[i];
+}
+
 // per state (one warp), after the matvec of iteration k:
 //   alpha_k = <w, V_k> (tdse.py:445,468) from the partial sums conj(w)*slab_k (times rinv_k),
 //   c^k = expm(fac T_k)[:,0] and dc = c^k - c^{k-1} (tdse.py:474-475); the coefficients are stored

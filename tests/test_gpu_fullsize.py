@@ -244,3 +244,31 @@ def test_dressed_init_state_with_device_eigensolver():
     for row in b:
         u = row / np.linalg.norm(row)
         assert np.linalg.norm(Hm @ u - np.vdot(u, Hm @ u) * u) < 1e-9 * np.abs(Hm).max()
+
+
+def test_small_exponential_against_scipy_expm():
+    """a4 (no direct test): `warp_expm_col0`, the routine behind `expm(fac*T_k)[:, 0]` (richmol/tdse.py:474),
+    through `rmb_small_expm` against `scipy.linalg.expm` -- all three paths: registers (n <= 32, one sub-step), registers with
+    sub-steps (half-width of the spectrum times |fac| up to ~40), shared memory (n > 32); a large common shift of the diagonal
+    (the isotropic polarisability term) that the routine splits off as a scalar phase; a complex `fac` with a damping part."""
+    import ctypes as C
+    from scipy.linalg import expm
+    from richmol_b200 import _lib
+    rng = np.random.default_rng(11)
+    lib = _lib.lib()
+    cases = [(2, 0.0, 30.0, -1.88e-3j), (9, -1400.0, 500.0, -1.88e-3j), (10, -1400.0, 500.0, -5e-2j), (32, 200.0, 3000.0, -1.88e-3j),
+             (33, -900.0, 400.0, -1.88e-3j), (60, 0.0, 2000.0, -4e-3j), (12, -50.0, 300.0, -2e-3j - 1e-4), (5, 0.0, 0.0, -1.88e-3j)]
+    for n, shift, spread, fac in cases:
+        nmat = 6
+        alpha = shift + spread * (rng.random((nmat, n)) - 0.5) + 1e-14 * rng.standard_normal((nmat, n)) * 1j
+        beta = np.zeros((nmat, n))
+        beta[:, 1:] = 0.3 * spread * rng.random((nmat, n - 1))
+        beta[0, n // 2] = 0.0                                   # a decoupled block (the zero-beta case of the recurrence)
+        out = np.zeros((nmat, n), dtype=np.complex128)
+        a = np.ascontiguousarray(alpha, dtype=np.complex128)
+        _lib.check(lib.rmb_small_expm(nmat, n, a.ctypes.data_as(C.c_void_p), beta.ctypes.data_as(C.c_void_p),
+                                      float(np.real(fac)), float(np.imag(fac)), out.ctypes.data_as(C.c_void_p), None))
+        for i in range(nmat):
+            T = np.diag(alpha[i]) + np.diag(beta[i, 1:], 1) + np.diag(beta[i, 1:], -1)
+            ref = expm(fac * T)[:, 0]
+            assert np.abs(out[i] - ref).max() < 2e-13 * max(1.0, np.abs(ref).max()), (n, shift, spread, fac, i)
