@@ -680,6 +680,13 @@ int32_t rmb_operator_create(const rmb_operator_desc* d, rmb_operator** out) {
     for (auto& it : itemsG) op->h_itemG_states.push_back(it.nst);
     op->nitems2 = (int)items2.size();
     for (auto& it : items2) op->h_item2_states.push_back(it.nst);
+    // <w,v> partial slots of a state: one per tiled item, then one per (DMMA item, m-tile)
+    op->dot_slots = op->nitems2;
+    for (auto& it : itemsG) {
+        it.pslot = op->dot_slots;
+        it.pad2 = 0;
+        op->dot_slots += it.mt;
+    }
     if (getenv("RMB_DEBUG")) {
         fprintf(stderr, "[rmb] tiled items %d (smem %zu B), DMMA items %d (smem %zu B), scalar items %zu\n",
                 op->nitems2, op->matvec2_smem, op->nitemsG, op->matvecG_smem, op->h_items.size());
@@ -1316,7 +1323,7 @@ static inline int lin_parts(const rmb_operator* op) {
 
 // the tiled kernel can fuse the <w, V_k> partial sums only if it covers every bra block
 static inline bool fused_dot(const rmb_operator* op) { return op->nitems == 0 && op->nitems2 + op->nitemsG > 0; }
-static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->nitems2 + op->nitemsG : op->W->nchunk; }
+static inline int dot_parts(const rmb_operator* op) { return fused_dot(op) ? op->dot_slots : op->W->nchunk; }
 
 // (re)allocate the per-state small arrays and the product vector for `cap` states
 static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
@@ -1330,7 +1337,7 @@ static int ensure_workspace(rmb_operator* op, long long cap, int maxorder) {
     op->W->nchunk = nchunks(op->np);
     int rc;
     const size_t vec = (size_t)cap * (size_t)op->np;
-    const size_t np = (size_t)std::max({op->W->nchunk, op->nitems2 + op->nitemsG, op->lin_npart});
+    const size_t np = (size_t)std::max({op->W->nchunk, op->dot_slots, op->lin_npart});
     if ((rc = ensure(&op->W->d_w, vec))) return rc;
     RMB_CUDA(cudaMemset(op->W->d_w, 0, vec * sizeof(cplx)));   // pad elements stay zero forever
     if ((rc = ensure(&op->W->d_alpha, (size_t)cap * maxorder))) return rc;

@@ -173,6 +173,7 @@ struct rmb_operator {
 
     // ---- fused single-launch Lanczos step (linear rotors, small N): row -> block tables
     bool fused_ok = false;
+    int dot_slots = 0;               // <w,v> partials per state written by the tiled / DMMA matvec epilogues
     int fused_lcap = 0;              // entries per bra block the fused kernel stages in shared memory (0: lists stay global)
     bool defer_error = false;        // multi-step mode: no per-step synchronisation for the maxorder flag
     int* d_row_blk = nullptr;
