@@ -1,5 +1,5 @@
 """GPU timeline of device-resident bench steps (CUPTI through torch.profiler; no profiler-timed number is a bench value):
-    python tools/gpu_timeline.py [workload] [steps]
+    python tools/gpu_timeline.py [workload] [steps] [nstates]
 Prints busy time per kernel, the idle time of the device between the first and the last kernel of the timed steps, and
 the largest gaps with the kernels on either side."""
 import collections
@@ -18,7 +18,7 @@ w = bench.WORKLOADS[wl]()
 m = bench.build_model(w)
 tdse = TDSE(t_end=1e6, dt=bench.DT)
 tdse._time_grid = (None, bench._Endless(bench.DT), None)
-rows = w.rows(m, 0, w.nstates)
+rows = w.rows(m, 0, int(sys.argv[3]) if len(sys.argv) > 3 else w.nstates)
 tensors = [t["tensor"] for t in m["terms"]]
 cos2 = m.get("cos2")
 v = torch.from_numpy(rows).cuda()
